@@ -1,0 +1,129 @@
+"""ctypes binding of libpcadv.so (the C ABI declared in include/pcadv.h).
+
+The library is built in-tree by ``_build.build()``.  There is no CPU or PyTorch
+fallback: if the shared object is missing or the device is not sm_100,
+``lib()`` raises and every op fails loudly.
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+MAX_SEG = 6
+F32, F16, BF16, I32, I64 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ENGINE_SIMT, ENGINE_TC = 0, 1
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("k", C.c_int32), ("dtype", C.c_int32)]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("n", C.c_int32), ("num_seg", C.c_int32),
+        ("seg", Seg * MAX_SEG),
+        ("w", C.c_void_p), ("ldw", C.c_int64), ("w_dtype", C.c_int32), ("engine", C.c_int32),
+        ("bias", C.c_void_p), ("group_bias", C.c_void_p), ("rows_per_group", C.c_int64),
+        ("addend", C.c_void_p), ("ld_addend", C.c_int64),
+        ("act", C.c_int32), ("slope", C.c_float),
+        ("mask", C.c_void_p), ("ld_mask", C.c_int64), ("mask_dtype", C.c_int32),
+        ("mask_act", C.c_int32), ("mask_slope", C.c_float), ("out_dtype", C.c_int32),
+        ("out_scale", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("colmax_key", C.c_void_p), ("rowmax_key", C.c_void_p),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("n", C.c_int32), ("num_seg", C.c_int32),
+        ("dz", C.c_void_p), ("ld_dz", C.c_int64), ("dz_dtype", C.c_int32), ("engine", C.c_int32),
+        ("seg", Seg * MAX_SEG),
+        ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("dbias", C.c_void_p),
+        ("dgroup_bias", C.c_void_p), ("rows_per_group", C.c_int64), ("scale", C.c_void_p),
+    ]
+
+
+class MaxBwdArgs(C.Structure):
+    _fields_ = [
+        ("groups", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("act", C.c_int32),
+        ("slope", C.c_float), ("x_dtype", C.c_int32), ("w_dtype", C.c_int32), ("reserved", C.c_int32),
+        ("rows_per_group", C.c_int64),
+        ("dg", C.c_void_p), ("gval", C.c_void_p), ("idx", C.c_void_p),
+        ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("dbias", C.c_void_p),
+        ("dx_acc", C.c_void_p), ("ld_dx", C.c_int64), ("scale", C.c_void_p),
+    ]
+
+
+# every symbol include/pcadv.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "pcadv_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "pcadv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "pcadv_max_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "pcadv_maxpool_bwd": (C.c_int, [C.POINTER(MaxBwdArgs), C.c_void_p]),
+    "pcadv_rowmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                   C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_int32, C.c_void_p]),
+    "pcadv_amax_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcadv_convert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "pcadv_transpose": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "pcadv_version": (C.c_int, []),
+    "pcadv_device_check": (C.c_int, []),
+    "pcadv_last_error": (C.c_char_p, []),
+    "pcadv_launch_count": (C.c_longlong, []),
+}
+
+_LIB = None
+_DEVICE_OK = False
+
+
+class PcadvError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """dlopen libpcadv.so and bind every declared symbol.  Needs no GPU."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise PcadvError("libpcadv.so is not built (%s); run __graft_entry__.build()" % path)
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def lib():
+    """The loaded library, after checking that the current device is sm_100."""
+    global _DEVICE_OK
+    l = load()
+    if not _DEVICE_OK:
+        import torch
+        if not torch.cuda.is_available():
+            raise PcadvError("libpcadv needs a CUDA device (sm_100a); there is no CPU fallback")
+        if l.pcadv_device_check() != 0:
+            raise PcadvError(l.pcadv_last_error().decode())
+        _DEVICE_OK = True
+    return l
+
+
+def check(rc):
+    if rc != 0:
+        raise PcadvError("libpcadv call failed (%d): %s" % (rc, load().pcadv_last_error().decode()))
+
+
+def launch_count():
+    return int(load().pcadv_launch_count())

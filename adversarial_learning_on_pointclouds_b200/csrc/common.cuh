@@ -1,0 +1,105 @@
+// Shared helpers for libpcadv.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/pcadv.h"
+
+namespace pcadv {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define PCADV_CHECK_ARG(cond, ...)            \
+  do {                                        \
+    if (!(cond)) {                            \
+      pcadv::set_error(__VA_ARGS__);          \
+      return 1;                               \
+    }                                         \
+  } while (0)
+
+#define PCADV_CUDA_OK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      pcadv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                       __FILE__, __LINE__);                                          \
+      return 2;                                                                      \
+    }                                                                                \
+  } while (0)
+
+#define PCADV_LAUNCHED()                                                             \
+  do {                                                                               \
+    pcadv::g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      pcadv::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                       __FILE__, __LINE__);                                          \
+      return 3;                                                                      \
+    }                                                                                \
+  } while (0)
+
+// ---- dtype-generic scalar access -------------------------------------------------
+__device__ __forceinline__ float ld_as_float(const void* p, int64_t i, int dtype) {
+  if (dtype == PCADV_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == PCADV_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+__device__ __forceinline__ void st_from_float(void* p, int64_t i, int dtype, float v) {
+  if (dtype == PCADV_F32) {
+    reinterpret_cast<float*>(p)[i] = v;
+  } else if (dtype == PCADV_F16) {
+    // saturate instead of producing inf: fp16 overflows at 65504
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  } else {
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__host__ __device__ __forceinline__ int dtype_size(int dtype) {
+  return dtype == PCADV_F32 ? 4 : 2;
+}
+
+// ---- activation helpers ----------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == PCADV_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == PCADV_ACT_LEAKY) return v > 0.f ? v : v * slope;
+  return v;
+}
+// derivative expressed through the saved OUTPUT y = act(z): ReLU' = [y > 0],
+// LeakyReLU' = [y > 0] ? 1 : slope (y > 0 <=> z > 0 for slope > 0).
+__device__ __forceinline__ float act_grad_from_output(float y, int act, float slope) {
+  if (act == PCADV_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == PCADV_ACT_LEAKY) return y > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// ---- packed (value, first index) max keys ----------------------------------------
+// Order-preserving map float -> uint32, then (bits << 32) | ~index so that a
+// 64-bit unsigned max picks the largest value and, among equals, the smallest
+// index (torch.max's first-occurrence rule).  Key 0 is below every finite value.
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
+  return (static_cast<unsigned long long>(float_to_ordered(v)) << 32) |
+         static_cast<unsigned long long>(0xffffffffu - idx);
+}
+__device__ __forceinline__ float key_value(unsigned long long k) {
+  return ordered_to_float(static_cast<uint32_t>(k >> 32));
+}
+__device__ __forceinline__ uint32_t key_index(unsigned long long k) {
+  return 0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull);
+}
+
+}  // namespace pcadv

@@ -1,0 +1,378 @@
+// fp32-FFMA (CUDA-core) GEMM kernels: the fp32-accumulate verification mode of
+// every layer, and the production path of the layers that are too small or too
+// unaligned for tensor cores (K = 3 first layer, per-cloud heads with M = B
+// rows, K = 50 discriminator inputs).
+#include "common.cuh"
+
+namespace pcadv {
+
+namespace {
+
+constexpr int BM = 128;   // rows (points) per CTA
+constexpr int BN = 64;    // output channels per CTA
+constexpr int BK = 16;    // K chunk
+constexpr int AS_LD = BM + 4;
+constexpr int BS_LD = BN + 4;
+
+// ---- tile loaders: 8 (A) / 4 (W) consecutive k elements per thread ---------------
+template <int NV>
+__device__ __forceinline__ void load_k_run(const void* base, int dtype, int64_t row_off, int k0,
+                                           int kmax, bool row_ok, float (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = 0.f;
+  if (!row_ok) return;
+  if (dtype == PCADV_F32) {
+    const float* p = reinterpret_cast<const float*>(base) + row_off;
+    if (k0 + NV <= kmax && ((reinterpret_cast<uintptr_t>(p + k0) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(p + k0 + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (k0 + i < kmax) v[i] = __ldg(p + k0 + i);
+    }
+  } else if (dtype == PCADV_F16) {
+    const __half* p = reinterpret_cast<const __half*>(base) + row_off;
+    if (k0 + NV <= kmax && ((reinterpret_cast<uintptr_t>(p + k0) & (NV * 2 - 1)) == 0)) {
+      if constexpr (NV == 8) {
+        uint4 t = *reinterpret_cast<const uint4*>(p + k0);
+        const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+      } else {
+        uint2 t = *reinterpret_cast<const uint2*>(p + k0);
+        const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (k0 + i < kmax) v[i] = __half2float(p[k0 + i]);
+    }
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + row_off;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (k0 + i < kmax) v[i] = __bfloat162float(p[k0 + i]);
+  }
+}
+
+// =====================================================================================
+// out[r, c] = post(sum_k A[r, k] W[c, k] + ...), see pcadv_linear in pcadv.h
+// =====================================================================================
+__global__ void __launch_bounds__(256) simt_linear_kernel(const pcadv_linear_args a) {
+  __shared__ __align__(16) float As[BK][AS_LD];
+  __shared__ __align__(16) float Bs[BK][BS_LD];
+  __shared__ unsigned long long red_keys[16][BN];
+
+  const int t = threadIdx.x;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
+  const int col0 = blockIdx.y * BN;
+
+  const int arow = t >> 1, ak = (t & 1) * 8;
+  const int wn = t >> 2, wk = (t & 3) * 4;
+  const int ty = t >> 4, tx = t & 15;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int64_t grow = row0 + arow;
+  const bool arow_ok = grow < a.rows;
+  const int gcol = col0 + wn;
+  const bool wcol_ok = gcol < a.n;
+
+  int koff = 0;
+  for (int s = 0; s < a.num_seg; ++s) {
+    const pcadv_seg sg = a.seg[s];
+    for (int k0 = 0; k0 < sg.k; k0 += BK) {
+      float av[8], wv[4];
+      load_k_run<8>(sg.ptr, sg.dtype, grow * sg.ld, k0 + ak, sg.k, arow_ok, av);
+      load_k_run<4>(a.w, a.w_dtype, static_cast<int64_t>(gcol) * a.ldw + koff, k0 + wk, sg.k,
+                    wcol_ok, wv);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[ak + i][arow] = av[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[wk + i][wn] = wv[i];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float br[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+    koff += sg.k;
+  }
+
+  // ---- epilogue -----------------------------------------------------------------
+  const float oscale = a.out_scale ? *a.out_scale : 1.f;
+  const int64_t rpg = a.rows_per_group > 0 ? a.rows_per_group : a.rows;
+  const int64_t last_row = (row0 + BM - 1 < a.rows ? row0 + BM - 1 : a.rows - 1);
+  const bool one_group = (row0 / rpg) == (last_row / rpg);
+
+  unsigned long long ckey[4] = {0ull, 0ull, 0ull, 0ull};
+  int64_t cgroup = -1;
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + ty * 8 + i;
+    const bool r_ok = r < a.rows;
+    const int64_t g = r_ok ? r / rpg : 0;
+    if (a.colmax_key && r_ok && !one_group && g != cgroup) {
+      if (cgroup >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = col0 + tx * 4 + j;
+          if (c < a.n && ckey[j]) atomicMax(&a.colmax_key[cgroup * a.n + c], ckey[j]);
+          ckey[j] = 0ull;
+        }
+      }
+      cgroup = g;
+    }
+    unsigned long long rkey = 0ull;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx * 4 + j;
+      if (!r_ok || c >= a.n) continue;
+      float v = acc[i][j];
+      if (a.bias) v += a.bias[c];
+      if (a.group_bias) v += a.group_bias[g * a.n + c];
+      if (a.addend) v += a.addend[r * a.ld_addend + c];
+      const float pre = v;
+      v = apply_act(v, a.act, a.slope);
+      if (a.mask)
+        v *= act_grad_from_output(ld_as_float(a.mask, r * a.ld_mask + c, a.mask_dtype), a.mask_act,
+                                  a.mask_slope);
+      v *= oscale;
+      if (a.out) st_from_float(a.out, r * a.ld_out + c, a.out_dtype, v);
+      if (a.colmax_key) {
+        const unsigned long long k = pack_key(pre, static_cast<uint32_t>(r - g * rpg));
+        ckey[j] = k > ckey[j] ? k : ckey[j];
+      }
+      if (a.rowmax_key) {
+        const unsigned long long k = pack_key(pre, static_cast<uint32_t>(c));
+        rkey = k > rkey ? k : rkey;
+      }
+    }
+    if (a.rowmax_key) {
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, rkey, o);
+        rkey = other > rkey ? other : rkey;
+      }
+      if (tx == 0 && r_ok && rkey) atomicMax(&a.rowmax_key[r], rkey);
+    }
+  }
+
+  if (a.colmax_key) {
+    if (one_group) {
+      const int64_t g = row0 / rpg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red_keys[ty][tx * 4 + j] = ckey[j];
+      __syncthreads();
+      if (t < BN) {
+        unsigned long long k = 0ull;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) k = red_keys[q][t] > k ? red_keys[q][t] : k;
+        const int c = col0 + t;
+        if (c < a.n && k) atomicMax(&a.colmax_key[g * a.n + c], k);
+      }
+    } else if (cgroup >= 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = col0 + tx * 4 + j;
+        if (c < a.n && ckey[j]) atomicMax(&a.colmax_key[cgroup * a.n + c], ckey[j]);
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// dw[c, koff + k] += scale * sum_r dz[r, c] * x[r, k]   (split over rows, fp32 atomics)
+// =====================================================================================
+constexpr int WT = 64;   // output tile: 64 (c) x 64 (k)
+constexpr int WR = 16;   // rows per smem stage
+
+__global__ void __launch_bounds__(256) simt_wgrad_kernel(const pcadv_wgrad_args a, int seg_index,
+                                                        int koff, int64_t rows_per_split) {
+  __shared__ __align__(16) float Zs[WR][WT + 4];
+  __shared__ __align__(16) float Xs[WR][WT + 4];
+  const pcadv_seg sg = a.seg[seg_index];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * WT;
+  const int k0 = blockIdx.y * WT;
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.z) * rows_per_split;
+  const int64_t r_end = r_begin + rows_per_split < a.rows ? r_begin + rows_per_split : a.rows;
+
+  const int lr = t >> 4, l4 = (t & 15) * 4;   // loader: row lr, 4 consecutive columns
+  const int ty = t >> 4, tx = t & 15;         // compute: c = ty*4+i, k = tx*4+j
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_bias = a.dbias != nullptr && blockIdx.y == 0 && seg_index == 0 && tx == 0;
+
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += WR) {
+    float zv[4], xv[4];
+    const int64_t r = r0 + lr;
+    const bool ok = r < r_end;
+    load_k_run<4>(a.dz, a.dz_dtype, r * a.ld_dz, c0 + l4, a.n, ok, zv);
+    load_k_run<4>(sg.ptr, sg.dtype, r * sg.ld, k0 + l4, sg.k, ok, xv);
+    __syncthreads();
+    *reinterpret_cast<float4*>(&Zs[lr][l4]) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    *reinterpret_cast<float4*>(&Xs[lr][l4]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < WR; ++q) {
+      const float4 z = *reinterpret_cast<const float4*>(&Zs[q][ty * 4]);
+      const float4 x = *reinterpret_cast<const float4*>(&Xs[q][tx * 4]);
+      const float zr[4] = {z.x, z.y, z.z, z.w};
+      const float xr[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(zr[i], xr[j], acc[i][j]);
+        bsum[i] += zr[i];
+      }
+    }
+  }
+  const float sc = a.scale ? *a.scale : 1.f;
+  if (a.dw) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty * 4 + i;
+      if (c >= a.n) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + tx * 4 + j;
+        if (k < sg.k) atomicAdd(&a.dw[static_cast<int64_t>(c) * a.ld_dw + koff + k], acc[i][j] * sc);
+      }
+    }
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty * 4 + i;
+      if (c < a.n) atomicAdd(&a.dbias[c], bsum[i] * sc);
+    }
+  }
+}
+
+// dbias only (no segments): column sums of dz, split over rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const void* dz, int dz_dtype, int64_t ld,
+                                                    int64_t rows, int n, int64_t rows_per_split,
+                                                    const float* scale, float* out) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int sub = threadIdx.x >> 6;
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.y) * rows_per_split;
+  const int64_t r_end = r_begin + rows_per_split < rows ? r_begin + rows_per_split : rows;
+  float s = 0.f;
+  if (c < n)
+    for (int64_t r = r_begin + sub; r < r_end; r += 4) s += ld_as_float(dz, r * ld + c, dz_dtype);
+  red[sub][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (sub == 0 && c < n) {
+    s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    atomicAdd(&out[c], s * (scale ? *scale : 1.f));
+  }
+}
+
+// dgroup_bias[g, c] += sum_{r in cloud g} dz[r, c]
+__global__ void __launch_bounds__(256) group_colsum_kernel(const void* dz, int dz_dtype, int64_t ld,
+                                                          int n, int64_t rows_per_group,
+                                                          float* out) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int sub = threadIdx.x >> 6;
+  const int64_t g = blockIdx.y;
+  const int64_t r_begin = g * rows_per_group, r_end = r_begin + rows_per_group;
+  float s = 0.f;
+  if (c < n)
+    for (int64_t r = r_begin + sub; r < r_end; r += 4) s += ld_as_float(dz, r * ld + c, dz_dtype);
+  red[sub][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (sub == 0 && c < n) {
+    s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    out[g * n + c] += s;
+  }
+}
+
+}  // namespace
+
+int simt_linear(const pcadv_linear_args& a, cudaStream_t s) {
+  const int64_t tiles_m = (a.rows + BM - 1) / BM;
+  PCADV_CHECK_ARG(tiles_m <= 0x7fffffffLL, "pcadv_linear: too many rows");
+  dim3 grid(static_cast<unsigned>(tiles_m), (a.n + BN - 1) / BN);
+  simt_linear_kernel<<<grid, 256, 0, s>>>(a);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+int launch_group_colsum(const void* dz, int dz_dtype, int64_t ld, int64_t rows, int n,
+                        int64_t rows_per_group, float* out, cudaStream_t s) {
+  PCADV_CHECK_ARG(rows % rows_per_group == 0, "rows (%lld) not a multiple of rows_per_group (%lld)",
+                  (long long)rows, (long long)rows_per_group);
+  dim3 grid((n + 63) / 64, static_cast<unsigned>(rows / rows_per_group));
+  group_colsum_kernel<<<grid, 256, 0, s>>>(dz, dz_dtype, ld, n, rows_per_group, out);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+int launch_colsum(const void* dz, int dz_dtype, int64_t ld, int64_t rows, int n, const float* scale,
+                  float* out, cudaStream_t s) {
+  int64_t splits = (rows + 4095) / 4096;
+  if (splits > 1024) splits = 1024;
+  const int64_t rps = (rows + splits - 1) / splits;
+  dim3 grid((n + 63) / 64, static_cast<unsigned>((rows + rps - 1) / rps));
+  colsum_kernel<<<grid, 256, 0, s>>>(dz, dz_dtype, ld, rows, n, rps, scale, out);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+int simt_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
+  if (a.dw) {
+    int koff = 0;
+    for (int i = 0; i < a.num_seg; ++i) {
+      const int tiles = ((a.n + WT - 1) / WT) * ((a.seg[i].k + WT - 1) / WT);
+      int64_t splits = (148 * 8 + tiles - 1) / tiles;
+      const int64_t max_splits = (a.rows + 255) / 256;
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+      int64_t rps = (a.rows + splits - 1) / splits;
+      rps = (rps + WR - 1) / WR * WR;
+      dim3 grid((a.n + WT - 1) / WT, (a.seg[i].k + WT - 1) / WT,
+                static_cast<unsigned>((a.rows + rps - 1) / rps));
+      simt_wgrad_kernel<<<grid, 256, 0, s>>>(a, i, koff, rps);
+      PCADV_LAUNCHED();
+      koff += a.seg[i].k;
+    }
+  } else if (a.dbias) {
+    int rc = launch_colsum(a.dz, a.dz_dtype, a.ld_dz, a.rows, a.n, a.scale, a.dbias, s);
+    if (rc) return rc;
+  }
+  if (a.dgroup_bias) {
+    int rc = launch_group_colsum(a.dz, a.dz_dtype, a.ld_dz, a.rows, a.n, a.rows_per_group,
+                                 a.dgroup_bias, s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace pcadv

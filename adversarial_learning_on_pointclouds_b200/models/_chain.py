@@ -1,0 +1,136 @@
+"""Forward / backward of a chain of pointwise layers on libpcadv ops.
+
+A *chain* is what the reference writes as ``F.relu(self.convK(x))`` /
+``F.relu(self.fcK(x))`` sequences (models/pointnet.py:291-301, :308-314;
+models/discriminator.py:22-24, :44-48, :64-67).  Activations are point-major
+``[rows, channels]`` matrices; ``dz`` always means the gradient with respect
+to a layer's PRE-activation output, which is what dgrad and wgrad consume.
+"""
+import torch
+
+from .. import ops
+from ..ops import ACT_NONE, ENGINE_TC
+
+
+class Layer:
+    """One pointwise layer: y = act(x W^T + b)."""
+
+    __slots__ = ("w", "b", "act", "slope")
+
+    def __init__(self, w, b, act=ACT_NONE, slope=0.0):
+        self.w = w.reshape(w.shape[0], -1)      # Conv1d [Cout, Cin, 1] -> [Cout, Cin]
+        self.b = b
+        self.act = act
+        self.slope = slope
+
+
+def compute_weight(prec, w32, k_list, n):
+    """The copy of a weight matrix the engine multiplies with: a 16-bit copy when
+    the tensor-core engine can take the shape, else the fp32 master."""
+    if prec.engine == ENGINE_TC and all(k % 64 == 0 for k in k_list) and n % 16 == 0:
+        return w32.to(prec.act_dtype)
+    return w32
+
+
+def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, group_bias=None):
+    """Run ``layers`` on the K-concat of ``x_segs``.  ``group_bias`` (per-cloud
+    bias) applies to the first layer.  Returns the list of layer outputs."""
+    ys = []
+    segs = list(x_segs)
+    for i, L in enumerate(layers):
+        last = i == len(layers) - 1
+        w = compute_weight(prec, L.w, [s.shape[1] for s in segs], L.w.shape[0])
+        out_dtype = torch.float32 if (last and final_fp32) else prec.act_dtype
+        y, _, _ = ops.linear(segs, w, bias=L.b, act=L.act, slope=L.slope, out_dtype=out_dtype,
+                             engine=prec.engine, rows_per_group=rows_per_group if i == 0 else 0,
+                             group_bias=group_bias if i == 0 else None)
+        ys.append(y)
+        segs = [y]
+    return ys
+
+
+def pad_cols(t, mult=64):
+    """Zero-pad the column count of a small weight matrix to a multiple of ``mult``."""
+    n = t.shape[1]
+    if n % mult == 0:
+        return t
+    out = t.new_zeros((t.shape[0], (n + mult - 1) // mult * mult))
+    out[:, :n] = t
+    return out
+
+
+def prepare_dz(prec, dy, scale2, mask=None, mask_act=ACT_NONE, mask_slope=0.0):
+    """Turn an incoming fp32 gradient [rows, n] (with respect to a layer's OUTPUT)
+    into the dz the backward chain consumes: multiplied by act'(mask) when the
+    layer has an activation; in 16-bit mode also scaled by S, converted to the
+    activation dtype and zero-padded to a multiple of 64 columns."""
+    if not prec.scaled:
+        if mask is None or mask_act == ACT_NONE:
+            return dy
+        return ops.convert(dy, torch.float32, mask=mask, mask_act=mask_act, mask_slope=mask_slope)
+    n = dy.shape[1]
+    if mask_act == ACT_NONE:
+        mask = None
+    return ops.convert(dy, prec.act_dtype, cols_pad=(n + 63) // 64 * 64, scale=scale2[0:1],
+                       mask=mask, mask_act=mask_act, mask_slope=mask_slope)
+
+
+def dgrad_weight(prec, blocks, n_out):
+    """Weight of a dgrad GEMM: the K-concat of transposed forward weights.
+    ``blocks`` = list of [Cout_i, n_out] forward-weight slices (fp32); the result
+    is [n_out, sum(pad64(Cout_i))] in the compute dtype."""
+    parts = []
+    for wb in blocks:
+        t = wb.t()
+        parts.append(pad_cols(t) if prec.scaled else t)
+    wt = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
+    wt = wt.contiguous()
+    if prec.engine == ENGINE_TC and n_out % 16 == 0 and wt.shape[1] % 64 == 0:
+        return wt.to(prec.act_dtype)
+    return wt
+
+
+def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0):
+    """fp32 (dw, db) of one layer from its dz and input segments.  ``dz`` may carry
+    zero-padded columns beyond w_shape[0]."""
+    if not (need_w or need_b):
+        return None, None
+    n_pad = dz.shape[1]
+    dev = dz.device
+    ktot = sum(s.shape[1] for s in x_segs)
+    dw = torch.zeros((n_pad, ktot + extra_cols), dtype=torch.float32, device=dev) if need_w else None
+    db = torch.zeros((n_pad,), dtype=torch.float32, device=dev) if need_b else None
+    inv = scale2[1:2] if scale2 is not None else None
+    ops.wgrad(dz, x_segs if need_w else [], dw=dw[:, :ktot] if need_w else None, dbias=db, scale=inv,
+              engine=prec.engine)
+    n = w_shape[0]
+    return (dw[:n] if need_w else None), (db[:n] if need_b else None)
+
+
+def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, scale2, addends=None):
+    """Backward through a chain.  ``dz_last``: dz of the last layer ([rows, pad(n)]).
+    ``need_w[i]`` / ``need_b[i]``: which parameter gradients to form (frozen
+    discriminators skip wgrad, utils/trainer.py:885-886).  Returns
+    (list of (dw, db), dx, dz0) where dx is the fp32, UNSCALED gradient of the chain
+    input (only when ``need_x``; single input segment) and dz0 the (scaled) dz of
+    the first layer."""
+    grads = [None] * len(layers)
+    dz = dz_last
+    for i in range(len(layers) - 1, -1, -1):
+        L = layers[i]
+        xin = x_segs if i == 0 else [ys[i - 1]]
+        grads[i] = layer_wgrad(prec, dz, xin, L.w.shape, need_w[i], need_b[i], scale2)
+        if i == 0:
+            break
+        P = layers[i - 1]
+        wt = dgrad_weight(prec, [L.w], L.w.shape[1])
+        dz, _, _ = ops.linear([dz], wt, mask=ys[i - 1], mask_act=P.act, mask_slope=P.slope,
+                              out_dtype=prec.act_dtype, engine=prec.engine,
+                              addend=addends.get(i - 1))
+    dx = None
+    if need_x:
+        L = layers[0]
+        wt = dgrad_weight(prec, [L.w], L.w.shape[1])
+        inv = scale2[1:2] if scale2 is not None else None
+        dx, _, _ = ops.linear([dz], wt, out_dtype=torch.float32, out_scale=inv, engine=prec.engine)
+    return grads, dx, dz

@@ -1,0 +1,266 @@
+"""Generic autograd Functions on libpcadv ops: a chain of pointwise layers with
+an optional fused reduction (max over the cloud's points, or over channels), the
+per-cloud T-Net transform, and the orthogonality regulariser.
+
+Tensors that cross a Function boundary are fp32; inside, activations live in the
+precision mode's storage dtype and gradients carry a dynamic power-of-two scale.
+"""
+import torch
+
+from .. import ops
+from ..ops import ACT_NONE, ENGINE_SIMT
+from ._chain import (Layer, chain_forward, chain_backward, compute_weight, prepare_dz, layer_wgrad,
+                     dgrad_weight)
+
+
+class MLPSpec:
+    """Static description of a PointMLPFunction call.
+
+    acts    : [(act, slope)] per layer
+    reduce  : None | "points" (max over each cloud's ``group`` rows of the last
+              layer, models/pointnet.py:31/:129/:303) | "channels" (max over the
+              last layer's channels per row, models/discriminator.py:71)
+    group   : rows per cloud (needed for reduce="points")
+    tap     : index of a layer whose output is also returned (fp32) -- the
+              ``pointfeat`` of models/pointnet.py:124 -- or None
+    A per-cloud bias ``gb`` [rows / group, n0] may be added to the first layer (the
+    folded tiled-global-feature columns of models/pointnet.py:135-136).
+    """
+
+    def __init__(self, acts, reduce=None, group=0, tap=None):
+        self.acts, self.reduce, self.group, self.tap = list(acts), reduce, int(group), tap
+
+
+class PointMLPFunction(torch.autograd.Function):
+    """(x [rows, k] fp32, gb | None, *[w_i, b_i]) -> out fp32 (+ tap fp32).
+
+    out is [rows, n] (reduce=None), [rows / group, n] (reduce="points") or [rows]
+    (reduce="channels")."""
+
+    @staticmethod
+    def forward(ctx, prec, spec, x, gb, *params):
+        if not x.is_cuda:
+            raise RuntimeError("libpcadv layers need CUDA tensors; there is no CPU path")
+        if x.dim() != 2:
+            raise ValueError("PointMLPFunction expects [rows, k]")
+        if x.dtype != torch.float32 or x.stride(1) != 1:
+            x = x.contiguous().float()
+        nl = len(spec.acts)
+        layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
+        x_in = x
+        if prec.scaled and x.shape[1] % 64 == 0 and x.shape[0] >= 128:
+            x_in = ops.convert(x, prec.act_dtype)            # 16-bit copy feeds the tensor cores
+        body = layers if spec.reduce is None else layers[:-1]
+        if gb is not None:
+            gb = gb.contiguous().float()
+        ys = chain_forward(prec, [x_in], body, final_fp32=(spec.reduce is None),
+                           rows_per_group=spec.group if gb is not None else 0,
+                           group_bias=gb) if body else []
+        red_val = red_idx = None
+        if spec.reduce is not None:
+            L = layers[-1]
+            src = ys[-1] if ys else x_in
+            w = compute_weight(prec, L.w, [src.shape[1]], L.w.shape[0])
+            _, ckey, rkey = ops.linear([src], w, bias=L.b, want_out=False,
+                                       colmax=spec.reduce == "points",
+                                       rowmax=spec.reduce == "channels",
+                                       rows_per_group=spec.group, engine=prec.engine)
+            red_val, red_idx = ops.max_finalize(ckey if ckey is not None else rkey, L.act, L.slope)
+            out = red_val
+        else:
+            out = ys[-1]
+        tap = ys[spec.tap].float() if spec.tap is not None else None
+        ctx.prec, ctx.spec = prec, spec
+        ctx.n_ys = len(ys)
+        ctx.has_red = red_val is not None
+        ctx.has_gb = gb is not None
+        saved = [x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) + list(params)
+        ctx.save_for_backward(*saved)
+        if tap is not None:
+            return out, tap
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out, d_tap=None):
+        prec, spec = ctx.prec, ctx.spec
+        sv = list(ctx.saved_tensors)
+        x_in, ys = sv[0], sv[1:1 + ctx.n_ys]
+        pos = 1 + ctx.n_ys
+        red_val = red_idx = None
+        if ctx.has_red:
+            red_val, red_idx = sv[pos], sv[pos + 1]
+            pos += 2
+        params = sv[pos:]
+        nl = len(spec.acts)
+        layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
+        need = ctx.needs_input_grad[4:]
+        need_w = [need[2 * i] for i in range(nl)]
+        need_b = [need[2 * i + 1] for i in range(nl)]
+        need_x = ctx.needs_input_grad[2]
+        dev = x_in.device
+        grads = [(None, None)] * nl
+
+        srcs = []
+        if d_out is not None:
+            d_out = d_out.contiguous().float()
+            srcs.append(d_out.reshape(d_out.shape[0], -1))
+        if d_tap is not None:
+            d_tap = d_tap.contiguous().float()
+            srcs.append(d_tap)
+        if not srcs:
+            return (None,) * (4 + 2 * nl)
+        scale2 = ops.amax_scale(srcs) if prec.scaled else None
+        S = scale2[0:1] if prec.scaled else None
+        inv = scale2[1:2] if prec.scaled else None
+
+        addends = {}
+        if d_tap is not None:
+            addends[spec.tap] = d_tap * S if prec.scaled else d_tap
+
+        body = layers if spec.reduce is None else layers[:-1]
+        dz_last = None
+        dx = dz0 = None
+        if spec.reduce is None:
+            if d_out is not None:
+                L = layers[-1]
+                dz_last = prepare_dz(prec, d_out, scale2, mask=ys[-1], mask_act=L.act,
+                                     mask_slope=L.slope)
+        elif d_out is not None:
+            L = layers[-1]
+            src = ys[-1] if ys else x_in
+            if spec.reduce == "channels":
+                n = L.w.shape[0]
+                dz_red = ops.rowmax_bwd(d_out.reshape(-1), red_val, red_idx, n, act=L.act,
+                                        slope=L.slope, scale=S, out_dtype=prec.act_dtype)
+                grads[-1] = layer_wgrad(prec, dz_red, [src], L.w.shape, need_w[-1], need_b[-1], scale2)
+                if body or need_x:
+                    wt = dgrad_weight(prec, [L.w], L.w.shape[1])
+                    if body:
+                        P_ = body[-1]
+                        dz_last, _, _ = ops.linear([dz_red], wt, mask=src, mask_act=P_.act,
+                                                   mask_slope=P_.slope, out_dtype=prec.act_dtype,
+                                                   engine=prec.engine,
+                                                   addend=addends.pop(len(body) - 1, None))
+                    else:
+                        dx, _, _ = ops.linear([dz_red], wt, out_scale=inv, engine=prec.engine)
+            else:   # max over the cloud's points: sparse backward through the saved argmax
+                n, k = L.w.shape
+                dg = d_out * S if prec.scaled else d_out
+                dw = torch.zeros((n, k), dtype=torch.float32, device=dev) if need_w[-1] else None
+                db = torch.zeros((n,), dtype=torch.float32, device=dev) if need_b[-1] else None
+                dx_acc = None
+                if body or need_x:
+                    dx_acc = torch.zeros((src.shape[0], k), dtype=torch.float32, device=dev)
+                ops.maxpool_bwd(dg.contiguous(), red_val, red_idx, src, L.w, spec.group, act=L.act,
+                                slope=L.slope, dw=dw, dbias=db, dx_acc=dx_acc, scale=inv)
+                grads[-1] = (dw, db)
+                if body:
+                    P_ = body[-1]
+                    ad = addends.pop(len(body) - 1, None)
+                    if ad is not None:
+                        dx_acc = dx_acc + ad
+                    dz_last = ops.convert(dx_acc, prec.act_dtype, mask=src, mask_act=P_.act,
+                                          mask_slope=P_.slope)
+                elif need_x:
+                    dx = dx_acc * inv if prec.scaled else dx_acc
+        if body and dz_last is None and addends:
+            # only the tap carries gradient: start the chain at the tapped layer
+            t = spec.tap
+            P_ = body[t]
+            dz_t = ops.convert(addends.pop(t), prec.act_dtype, mask=ys[t], mask_act=P_.act,
+                               mask_slope=P_.slope)
+            g2, dx, dz0 = chain_backward(prec, dz_t, [x_in], ys[:t + 1], body[:t + 1],
+                                         need_w[:t + 1], need_b[:t + 1], need_x, scale2)
+            for i, gr in enumerate(g2):
+                grads[i] = gr
+        elif body and dz_last is not None:
+            g2, dx, dz0 = chain_backward(prec, dz_last, [x_in], ys[:len(body)], body,
+                                         need_w[:len(body)], need_b[:len(body)], need_x, scale2,
+                                         addends=addends)
+            for i, gr in enumerate(g2):
+                grads[i] = gr
+        dgb = None
+        if ctx.has_gb and ctx.needs_input_grad[3] and dz0 is not None:
+            rows, n0 = dz0.shape[0], layers[0].w.shape[0]
+            dgb = torch.zeros((rows // spec.group, dz0.shape[1]), dtype=torch.float32, device=dev)
+            ops.wgrad(dz0, [], dgroup_bias=dgb, rows_per_group=spec.group)
+            dgb = dgb[:, :n0] * inv if prec.scaled else dgb[:, :n0]
+        flat = []
+        for i in range(nl):
+            dw, db = grads[i] if grads[i] is not None else (None, None)
+            flat.append(dw.reshape(params[2 * i].shape) if dw is not None else None)
+            flat.append(db)
+        return (None, None, dx, dgb, *flat)
+
+
+def point_mlp(prec, x, layers, acts, reduce=None, group=0, tap=None, group_bias=None):
+    """Convenience wrapper: ``layers`` are nn.Conv1d / nn.Linear modules or
+    (weight, bias | None) pairs."""
+    params = []
+    for m in layers:
+        params += [m.weight, m.bias] if hasattr(m, "weight") else [m[0], m[1]]
+    return PointMLPFunction.apply(prec, MLPSpec(acts, reduce, group, tap), x, group_bias, *params)
+
+
+class BmmFunction(torch.autograd.Function):
+    """y[b] = x[b] @ T[b]: torch.bmm(x^T, trans) of models/pointnet.py:120-122 /
+    :231 / :238 on point-major x [B, N, k] (fp32) and T [B, k, k]."""
+
+    @staticmethod
+    def forward(ctx, x, trans):
+        B, N, k = x.shape
+        x = x.contiguous().float()
+        trans = trans.contiguous().float()
+        y = torch.empty_like(x)
+        for b in range(B):
+            wt = trans[b].t().contiguous()                  # out[r, c] = sum_k x[r, k] T[k, c]
+            y[b], _, _ = ops.linear([x[b]], wt, engine=ENGINE_SIMT)
+        ctx.save_for_backward(x, trans)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, trans = ctx.saved_tensors
+        B, N, k = x.shape
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dt = torch.zeros_like(trans) if ctx.needs_input_grad[1] else None
+        for b in range(B):
+            if dx is not None:                              # dx = dy @ T^T
+                dx[b], _, _ = ops.linear([dy[b]], trans[b], engine=ENGINE_SIMT)
+            if dt is not None:                              # dT[k, c] = sum_r x[r, k] dy[r, c]
+                ops.wgrad(x[b], [dy[b]], dw=dt[b])
+        return dx, dt
+
+
+class RegularizerFunction(torch.autograd.Function):
+    """mean_b || T T^T - I ||_F (models/pointnet.py:345-353)."""
+
+    @staticmethod
+    def forward(ctx, trans):
+        B, d, _ = trans.shape
+        t = trans.contiguous().float()
+        diff = torch.empty_like(t)
+        eye = torch.eye(d, dtype=torch.float32, device=t.device)
+        for b in range(B):                                  # (T T^T)[i, j] = sum_k T[i,k] T[j,k]
+            m, _, _ = ops.linear([t[b]], t[b], engine=ENGINE_SIMT)
+            diff[b] = m - eye
+        norms = diff.reshape(B, -1).norm(dim=1)
+        ctx.save_for_backward(t, diff, norms)
+        return norms.mean()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        t, diff, norms = ctx.saved_tensors
+        B = t.shape[0]
+        # d||M||_F / dM = M / ||M||;  M = T T^T - I  =>  dT = (G + G^T) T with G = dM
+        G = diff / norms.clamp_min(1e-30).view(B, 1, 1) * (dloss / B)
+        dT = torch.empty_like(t)
+        for b in range(B):
+            sym = (G[b] + G[b].t()).contiguous()
+            dT[b], _, _ = ops.linear([sym], t[b].t().contiguous(), engine=ENGINE_SIMT)
+        return dT
+
+
+__all__ = ["MLPSpec", "PointMLPFunction", "point_mlp", "BmmFunction", "RegularizerFunction",
+           "ACT_NONE"]

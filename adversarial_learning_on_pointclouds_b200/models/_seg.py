@@ -1,0 +1,162 @@
+"""PointNetSeg forward / backward as one autograd Function on libpcadv ops.
+
+Mirrors models/pointnet.py:282-317 of the reference with three structural
+changes that leave the mathematics unchanged:
+
+* the 2048-wide conv6 output is never written: the layer, its ReLU and the max
+  over the cloud's points run as one kernel that emits (max, first argmax);
+* the 3024-channel concat is never built: fc1 reads x1..x5 as five K-segments
+  and the tiled global-feature / class-one-hot columns become a per-cloud bias
+  ``fc1.W[:, 960:] @ [g; cls] + fc1.b``;
+* the backward through the max uses the saved argmax only (sparse scatter), and
+  each trunk layer's dgrad is one GEMM over the K-concat [dz_next | dz_fc1].
+"""
+import torch
+
+from .. import ops
+from ..ops import ACT_NONE, ACT_RELU, ENGINE_SIMT
+from ._chain import (Layer, chain_forward, compute_weight, dgrad_weight, layer_wgrad, prepare_dz)
+
+_TRUNK = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
+_HEAD = ("fc1", "fc2", "fc3", "fc4")
+PARAM_NAMES = tuple(n + s for n in _TRUNK + _HEAD for s in (".weight", ".bias"))
+_SLICES = ((0, 64), (64, 192), (192, 320), (320, 448), (448, 960))   # x1..x5 inside the concat
+_G0, _G1, _C1 = 960, 3008, 3024                                       # global / class columns
+
+
+class SegFunction(torch.autograd.Function):
+    """(pts [B,N,3], cls [B,1,16], *params) -> (logits [B,N,k] fp32, global [B,2048] fp32)."""
+
+    @staticmethod
+    def forward(ctx, prec, debug, pts, cls, *params):
+        if not pts.is_cuda:
+            raise RuntimeError("PointNetSeg (libpcadv) needs CUDA tensors; there is no CPU path")
+        p = dict(zip(PARAM_NAMES, params))
+        B, N, _ = pts.shape
+        P = B * N
+        pts2 = pts.reshape(P, 3).contiguous().float()
+        cls2 = cls.reshape(B, -1).contiguous().float()
+        W = {n: p[n + ".weight"].reshape(p[n + ".weight"].shape[0], -1) for n in _TRUNK + _HEAD}
+        b = {n: p[n + ".bias"] for n in _TRUNK + _HEAD}
+
+        # trunk: conv1 (K=3, CUDA-core, HBM-bound) then conv2..conv5
+        xs = chain_forward(prec, [pts2], [Layer(W[n], b[n], ACT_RELU) for n in _TRUNK[:5]])
+        x5 = xs[4]
+        # conv6 + ReLU + max over the cloud, fused; the B x 2048 x N map is never stored
+        w6 = compute_weight(prec, W["conv6"], [512], 2048)
+        _, key, _ = ops.linear([x5], w6, bias=b["conv6"], want_out=False, colmax=True,
+                               rows_per_group=N, engine=prec.engine)
+        g, idx = ops.max_finalize(key, ACT_RELU)
+        # fold the tiled global feature and class one-hot into a per-cloud bias
+        cbias, _, _ = ops.linear([g, cls2], W["fc1"][:, _G0:_C1], bias=b["fc1"], engine=ENGINE_SIMT)
+        hs = chain_forward(prec, xs, [Layer(W["fc1"][:, :_G0], None, ACT_RELU),
+                                      Layer(W["fc2"], b["fc2"], ACT_RELU),
+                                      Layer(W["fc3"], b["fc3"], ACT_RELU),
+                                      Layer(W["fc4"], b["fc4"], ACT_NONE)],
+                           final_fp32=True, rows_per_group=N, group_bias=cbias)
+        logits = hs[3].view(B, N, -1)
+
+        ctx.prec, ctx.shape = prec, (B, N)
+        ctx.save_for_backward(pts2, cls2, g, idx, *xs, *hs[:3], *params)
+        if debug is not None:
+            debug.update(x=xs, h=hs[:3], g=g, idx=idx, cbias=cbias)
+        return logits, g
+
+    @staticmethod
+    def backward(ctx, dlogits, dg_ext):
+        prec = ctx.prec
+        B, N = ctx.shape
+        P = B * N
+        sv = ctx.saved_tensors
+        pts2, cls2, g, idx = sv[0:4]
+        xs, hs, params = list(sv[4:9]), list(sv[9:12]), sv[12:]
+        p = dict(zip(PARAM_NAMES, params))
+        need = dict(zip(PARAM_NAMES, ctx.needs_input_grad[4:]))
+        W = {n: p[n + ".weight"].reshape(p[n + ".weight"].shape[0], -1) for n in _TRUNK + _HEAD}
+        dev = pts2.device
+        k_out = W["fc4"].shape[0]
+        grads = {}
+
+        if dlogits is None:
+            dlogits = torch.zeros((B, N, k_out), dtype=torch.float32, device=dev)
+        dl = dlogits.reshape(P, k_out)
+        if dl.stride(1) != 1 or dl.dtype != torch.float32:
+            dl = dl.contiguous().float()
+        scale2 = ops.amax_scale(dl) if prec.scaled else None
+        inv = scale2[1:2] if prec.scaled else None
+
+        # ---- head: fc4, fc3, fc2 ---------------------------------------------------
+        dz = prepare_dz(prec, dl, scale2)
+        head = (("fc4", ACT_NONE), ("fc3", ACT_RELU), ("fc2", ACT_RELU))
+        for li, (name, _) in enumerate(head):
+            xin = hs[2 - li]
+            dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
+                                 need[name + ".bias"], scale2)
+            grads[name + ".weight"], grads[name + ".bias"] = dw, db
+            wt = dgrad_weight(prec, [W[name]], W[name].shape[1])
+            dz, _, _ = ops.linear([dz], wt, mask=xin, mask_act=ACT_RELU, out_dtype=prec.act_dtype,
+                                  engine=prec.engine)
+        dz_fc1 = dz                                                   # [P, 256], scaled
+
+        # ---- fc1: per-point part (x1..x5) and per-cloud part (g, cls, bias) -----------
+        need_w1, need_b1 = need["fc1.weight"], need["fc1.bias"]
+        dw1 = torch.zeros((256, _C1), dtype=torch.float32, device=dev) if need_w1 else None
+        db1 = torch.zeros((256,), dtype=torch.float32, device=dev) if need_b1 else None
+        dcb = torch.zeros((B, 256), dtype=torch.float32, device=dev)   # d(cbias), scaled
+        ops.wgrad(dz_fc1, xs if need_w1 else [], dw=dw1[:, :_G0] if need_w1 else None,
+                  dgroup_bias=dcb, rows_per_group=N, scale=inv, engine=prec.engine)
+        if need_w1 or need_b1:
+            ops.wgrad(dcb, [g, cls2] if need_w1 else [], dw=dw1[:, _G0:_C1] if need_w1 else None,
+                      dbias=db1, scale=inv)
+        grads["fc1.weight"], grads["fc1.bias"] = dw1, db1
+
+        # ---- through the max: dg = dcbias @ fc1.W[:, 960:3008] (+ external grad) -------
+        wg_t = W["fc1"][:, _G0:_G1].t().contiguous()                  # [2048, 256]
+        dg, _, _ = ops.linear([dcb], wg_t, engine=ENGINE_SIMT)        # [B, 2048], scaled
+        if dg_ext is not None:
+            dg = dg + (dg_ext.float() * scale2[0] if prec.scaled else dg_ext.float())
+        dw6 = torch.zeros((2048, 512), dtype=torch.float32, device=dev) if need["conv6.weight"] else None
+        db6 = torch.zeros((2048,), dtype=torch.float32, device=dev) if need["conv6.bias"] else None
+        dx5_sparse = torch.zeros((P, 512), dtype=torch.float32, device=dev)
+        ops.maxpool_bwd(dg, g, idx, xs[4], W["conv6"], N, act=ACT_RELU, dw=dw6, dbias=db6,
+                        dx_acc=dx5_sparse, scale=inv)
+        grads["conv6.weight"], grads["conv6.bias"] = dw6, db6
+
+        # ---- trunk: dz_k = relu'(x_k) * ([dz_{k+1} | dz_fc1] @ [W_{k+1}; fc1.W[:, slice_k]]) --
+        s5 = _SLICES[4]
+        wt = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512)
+        dz, _, _ = ops.linear([dz_fc1], wt, addend=dx5_sparse, mask=xs[4], mask_act=ACT_RELU,
+                              out_dtype=prec.act_dtype, engine=prec.engine)
+        del dx5_sparse
+        for li in range(4, 0, -1):                                    # conv5 .. conv2
+            name = _TRUNK[li]
+            xin = xs[li - 1]
+            dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
+                                 need[name + ".bias"], scale2)
+            grads[name + ".weight"], grads[name + ".bias"] = dw, db
+            sl = _SLICES[li - 1]
+            wt = dgrad_weight(prec, [W[name], W["fc1"][:, sl[0]:sl[1]]], W[name].shape[1])
+            dz, _, _ = ops.linear([dz, dz_fc1], wt, mask=xin, mask_act=ACT_RELU,
+                                  out_dtype=prec.act_dtype, engine=prec.engine)
+        dw, db = layer_wgrad(prec, dz, [pts2], W["conv1"].shape, need["conv1.weight"],
+                             need["conv1.bias"], scale2)
+        grads["conv1.weight"], grads["conv1.bias"] = dw, db
+
+        dpts = None
+        if ctx.needs_input_grad[2]:
+            wt = W["conv1"].t().contiguous()                          # [3, 64]
+            dpts, _, _ = ops.linear([dz], wt, out_scale=inv, engine=ENGINE_SIMT)
+            dpts = dpts.view(B, N, 3)
+        dcls = None
+        if ctx.needs_input_grad[3]:
+            wc_t = W["fc1"][:, _G1:_C1].t().contiguous()              # [16, 256]
+            dcls, _, _ = ops.linear([dcb], wc_t, out_scale=inv, engine=ENGINE_SIMT)
+            dcls = dcls.view(B, 1, -1)
+
+        out = []
+        for n_ in PARAM_NAMES:
+            gr = grads.get(n_)
+            if gr is not None:
+                gr = gr.reshape(p[n_].shape)
+            out.append(gr)
+        return (None, None, dpts, dcls, *out)

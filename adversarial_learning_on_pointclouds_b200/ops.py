@@ -1,0 +1,273 @@
+"""Tensor-level wrappers over the libpcadv C ABI.
+
+torch is used here for device memory (torch.empty / torch.zeros), the current
+CUDA stream and dtype bookkeeping only; every arithmetic op is a libpcadv call.
+All matrices are point-major ``[rows, channels]`` with unit stride on channels.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ENGINE_SIMT, ENGINE_TC, F16, F32, BF16)
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+class Precision:
+    """Arithmetic mode of the per-point layers.
+
+    fp32 : fp32 storage, fp32 FFMA accumulation (verification mode, 1e-5).
+    fp16 : fp16 storage, tcgen05 kind::f16 with fp32 accumulation; gradients are
+           carried with a power-of-two dynamic scale (default fast mode, 1e-3).
+    bf16 : bf16 storage, same kernels (wide-range mode, ~1e-2).
+    """
+
+    def __init__(self, name):
+        if name not in ("fp32", "fp16", "bf16"):
+            raise ValueError("precision must be fp32, fp16 or bf16, got %r" % (name,))
+        self.name = name
+        self.act_dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[name]
+        self.scaled = name != "fp32"
+        want_tc = name != "fp32" and os.environ.get("PCADV_ENGINE", "tc") != "simt"
+        self.engine = ENGINE_TC if want_tc else ENGINE_SIMT
+
+    def __repr__(self):
+        return "Precision(%s)" % self.name
+
+
+_DEFAULT = [Precision(os.environ.get("PCADV_PRECISION", "fp16"))]
+
+
+def set_default_precision(name):
+    _DEFAULT[0] = Precision(name)
+
+
+def default_precision():
+    return _DEFAULT[0]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _mat(t):
+    """(ptr, ld, dtype code) of a 2-D tensor with unit column stride."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("expected a [rows, cols] tensor with unit column stride, got %s / %s"
+                         % (tuple(t.shape), t.stride()))
+    if not t.is_cuda:
+        raise RuntimeError("libpcadv ops need CUDA tensors (there is no CPU path)")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return C.c_void_p(t.data_ptr()), int(ld), _DT[t.dtype]
+
+
+def _f32(t, n=None):
+    if t is None:
+        return C.c_void_p(0)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("expected a contiguous fp32 tensor")
+    if n is not None and t.numel() != n:
+        raise ValueError("expected %d elements, got %d" % (n, t.numel()))
+    return C.c_void_p(t.data_ptr())
+
+
+def tc_eligible(segs, w, n):
+    """Shapes the tensor-core engine takes: 16-bit operands, every K segment a
+    multiple of 64 with 16-byte aligned rows."""
+    for s in segs:
+        if s.dtype not in (torch.float16, torch.bfloat16) or s.shape[1] % 64 or s.stride(0) % 8 \
+                or s.data_ptr() % 16:
+            return False
+    if w.dtype != segs[0].dtype or w.stride(0) % 8 or w.data_ptr() % 16:
+        return False
+    return n % 16 == 0 and segs[0].shape[0] >= 128
+
+
+def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None, act=ACT_NONE,
+           slope=0.0, mask=None, mask_act=ACT_NONE, mask_slope=0.0, out_dtype=torch.float32,
+           out_scale=None, want_out=True, colmax=False, rowmax=False, engine=ENGINE_SIMT, n=None):
+    """See ``pcadv_linear`` in include/pcadv.h.  Returns (out | None, colmax_key |
+    None, rowmax_key | None)."""
+    a = _lib.LinearArgs()
+    rows = segs[0].shape[0]
+    n = int(n if n is not None else w.shape[0])
+    a.rows, a.n, a.num_seg = rows, n, len(segs)
+    ktot = 0
+    for i, s in enumerate(segs):
+        if s.shape[0] != rows:
+            raise ValueError("segment %d has %d rows, expected %d" % (i, s.shape[0], rows))
+        p, ld, dt = _mat(s)
+        a.seg[i].ptr, a.seg[i].ld, a.seg[i].k, a.seg[i].dtype = p, ld, s.shape[1], dt
+        ktot += s.shape[1]
+    if w.shape[1] != ktot or w.shape[0] < n:
+        raise ValueError("weight %s does not match n=%d, ktot=%d" % (tuple(w.shape), n, ktot))
+    a.w, a.ldw, a.w_dtype = _mat(w)
+    if engine == ENGINE_TC and not tc_eligible(segs, w, n):
+        engine = ENGINE_SIMT
+    a.engine = engine
+    a.bias = _f32(bias, n) if bias is not None else None
+    dev = segs[0].device
+    if group_bias is not None:
+        if rows_per_group <= 0 or rows % rows_per_group:
+            raise ValueError("rows_per_group must divide rows")
+        a.group_bias = _f32(group_bias, (rows // rows_per_group) * n)
+    a.rows_per_group = int(rows_per_group)
+    if addend is not None:
+        p, ld, dt = _mat(addend)
+        if dt != F32:
+            raise ValueError("addend must be fp32")
+        a.addend, a.ld_addend = p, ld
+    a.act, a.slope = act, float(slope)
+    if mask is not None:
+        p, ld, dt = _mat(mask)
+        a.mask, a.ld_mask, a.mask_dtype = p, ld, dt
+        a.mask_act, a.mask_slope = mask_act, float(mask_slope)
+    a.out_scale = _f32(out_scale) if out_scale is not None else None
+    out = ckey = rkey = None
+    a.out_dtype = _DT[out_dtype]
+    if want_out:
+        out = torch.empty((rows, n), dtype=out_dtype, device=dev)
+        a.out, a.ld_out = C.c_void_p(out.data_ptr()), n
+    if colmax:
+        if rows_per_group <= 0 or rows % rows_per_group:
+            raise ValueError("colmax needs rows_per_group dividing rows")
+        ckey = torch.zeros((rows // rows_per_group, n), dtype=torch.int64, device=dev)
+        a.colmax_key = C.c_void_p(ckey.data_ptr())
+    if rowmax:
+        rkey = torch.zeros((rows,), dtype=torch.int64, device=dev)
+        a.rowmax_key = C.c_void_p(rkey.data_ptr())
+    _lib.check(_lib.lib().pcadv_linear(C.byref(a), _stream()))
+    return out, ckey, rkey
+
+
+def wgrad(dz, segs, *, dw=None, dbias=None, dgroup_bias=None, rows_per_group=0, scale=None,
+          engine=ENGINE_SIMT, n=None):
+    """See ``pcadv_wgrad``.  ``dw`` / ``dbias`` / ``dgroup_bias`` are fp32 tensors that
+    are accumulated into; ``dw`` may be a column-sliced view (unit column stride)."""
+    a = _lib.WgradArgs()
+    rows = dz.shape[0]
+    n = int(n if n is not None else dz.shape[1])
+    a.rows, a.n, a.num_seg = rows, n, len(segs)
+    a.dz, a.ld_dz, a.dz_dtype = _mat(dz)
+    ktot = 0
+    for i, s in enumerate(segs):
+        p, ld, dt = _mat(s)
+        if s.shape[0] != rows:
+            raise ValueError("segment %d has %d rows, expected %d" % (i, s.shape[0], rows))
+        a.seg[i].ptr, a.seg[i].ld, a.seg[i].k, a.seg[i].dtype = p, ld, s.shape[1], dt
+        ktot += s.shape[1]
+    if dw is not None:
+        p, ld, dt = _mat(dw)
+        if dt != F32 or dw.shape[0] < n or dw.shape[1] != ktot:
+            raise ValueError("dw must be fp32 [>=%d, %d], got %s" % (n, ktot, tuple(dw.shape)))
+        a.dw, a.ld_dw = p, ld
+    a.dbias = _f32(dbias) if dbias is not None else None
+    if dgroup_bias is not None:
+        a.dgroup_bias = _f32(dgroup_bias, (rows // rows_per_group) * n)
+    a.rows_per_group = int(rows_per_group)
+    a.scale = _f32(scale) if scale is not None else None
+    if engine == ENGINE_TC:
+        ok = dz.dtype in (torch.float16, torch.bfloat16) and n % 64 == 0 and rows >= 64 and \
+            all(s.dtype == dz.dtype and s.shape[1] % 64 == 0 and s.stride(0) % 8 == 0 for s in segs) \
+            and dz.stride(0) % 8 == 0 and dw is not None
+        if not ok:
+            engine = ENGINE_SIMT
+    a.engine = engine
+    _lib.check(_lib.lib().pcadv_wgrad(C.byref(a), _stream()))
+
+
+def max_finalize(key, act=ACT_NONE, slope=0.0, want_idx=True):
+    """Unpack packed max keys -> (val fp32, idx int32) with the shape of ``key``."""
+    val = torch.empty(key.shape, dtype=torch.float32, device=key.device)
+    idx = torch.empty(key.shape, dtype=torch.int32, device=key.device) if want_idx else None
+    _lib.check(_lib.lib().pcadv_max_finalize(_ptr(key), key.numel(), act, float(slope), _ptr(val),
+                                             _ptr(idx), _stream()))
+    return val, idx
+
+
+def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0, dw=None,
+                dbias=None, dx_acc=None, scale=None):
+    """See ``pcadv_maxpool_bwd``."""
+    a = _lib.MaxBwdArgs()
+    groups, n = dg.shape
+    a.groups, a.n, a.k = groups, n, w.shape[1]
+    a.act, a.slope = act, float(slope)
+    a.rows_per_group = int(rows_per_group)
+    a.dg, a.gval = _f32(dg, groups * n), _f32(gval, groups * n)
+    if idx.dtype != torch.int32 or not idx.is_contiguous():
+        raise ValueError("idx must be contiguous int32")
+    a.idx = _ptr(idx)
+    a.x, a.ldx, a.x_dtype = _mat(x)
+    a.w, a.ldw, a.w_dtype = _mat(w)
+    if dw is not None:
+        p, ld, dt = _mat(dw)
+        a.dw, a.ld_dw = p, ld
+    a.dbias = _f32(dbias) if dbias is not None else None
+    if dx_acc is not None:
+        p, ld, dt = _mat(dx_acc)
+        if dt != F32:
+            raise ValueError("dx_acc must be fp32")
+        a.dx_acc, a.ld_dx = p, ld
+    a.scale = _f32(scale) if scale is not None else None
+    _lib.check(_lib.lib().pcadv_maxpool_bwd(C.byref(a), _stream()))
+
+
+def rowmax_bwd(dy, val, idx, n, *, act=ACT_NONE, slope=0.0, scale=None, out_dtype=torch.float32):
+    rows = dy.numel()
+    dz = torch.empty((rows, n), dtype=out_dtype, device=dy.device)
+    _lib.check(_lib.lib().pcadv_rowmax_bwd(_f32(dy), _f32(val), _ptr(idx), rows, n, act, float(slope),
+                                           _f32(scale) if scale is not None else None, _ptr(dz), n,
+                                           _DT[out_dtype], _stream()))
+    return dz
+
+
+def amax_scale(xs, target=256.0):
+    """Device-side power-of-two gradient scale over one or several fp32 matrices:
+    returns a 2-float tensor [S, 1/S] with S = 2^floor(log2(target / max|x|))."""
+    if isinstance(xs, torch.Tensor):
+        xs = [xs]
+    dev = xs[0].device
+    ws = torch.zeros(1, dtype=torch.int32, device=dev)
+    s2 = torch.empty(2, dtype=torch.float32, device=dev)
+    for x in xs:
+        p, ld, dt = _mat(x)
+        if dt != F32:
+            raise ValueError("amax_scale expects fp32")
+        _lib.check(_lib.lib().pcadv_amax_scale(p, x.shape[0], x.shape[1], ld, float(target), _ptr(ws),
+                                               _ptr(s2), _stream()))
+    return s2
+
+
+def convert(src, out_dtype, cols_pad=None, scale=None, mask=None, mask_act=ACT_NONE, mask_slope=0.0):
+    """dst = convert(src * scale * act'(mask)), zero-padded to ``cols_pad`` columns."""
+    p, ld, dt = _mat(src)
+    rows, cols = src.shape
+    cols_pad = int(cols_pad or cols)
+    dst = torch.empty((rows, cols_pad), dtype=out_dtype, device=src.device)
+    mp, mld, mdt = _mat(mask) if mask is not None else (C.c_void_p(0), 0, F32)
+    _lib.check(_lib.lib().pcadv_convert(p, dt, ld, rows, cols, _ptr(dst), _DT[out_dtype], cols_pad,
+                                        cols_pad, _f32(scale) if scale is not None else None,
+                                        mp, mld, mdt, mask_act, float(mask_slope), _stream()))
+    return dst
+
+
+def transpose(src, out_dtype=None):
+    """dst[c, r] = src[r, c] (weight matrices only)."""
+    p, ld, dt = _mat(src)
+    out_dtype = out_dtype or src.dtype
+    rows, cols = src.shape
+    dst = torch.empty((cols, rows), dtype=out_dtype, device=src.device)
+    _lib.check(_lib.lib().pcadv_transpose(p, dt, ld, rows, cols, _ptr(dst), _DT[out_dtype], rows,
+                                          _stream()))
+    return dst
+
+
+__all__ = ["Precision", "set_default_precision", "default_precision", "linear", "wgrad",
+           "max_finalize", "maxpool_bwd", "rowmax_bwd", "amax_scale", "convert", "transpose",
+           "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ENGINE_SIMT", "ENGINE_TC"]

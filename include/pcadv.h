@@ -1,0 +1,206 @@
+/*
+ * pcadv.h -- C ABI of libpcadv.so, the sm_100a kernel library behind the
+ * PointNet + discriminator adversarial train step.
+ *
+ * The reference (YiruS/Adversarial_Learning_on_PointClouds) has no FFI layer:
+ * its hot path is the Python nn.Module API of models/pointnet.py and
+ * models/discriminator.py, whose arithmetic is ATen library calls
+ * (SURVEY.md 8b).  Each entry point below replaces one family of those calls;
+ * the reference line it stands in for is cited beside it.  The only callers are
+ * the torch.autograd.Function classes in
+ * adversarial_learning_on_pointclouds_b200/models/ (via ctypes, see
+ * INTEGRATION.md).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every pointer is a DEVICE pointer owned by
+ *     the caller (torch.empty); the library allocates nothing persistent.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*).  No
+ *     entry point synchronises the device.
+ *   - Return 0 on success, non-zero on failure; pcadv_last_error() returns a
+ *     thread-local message.  Nothing throws across the ABI, nothing calls exit.
+ *   - "rows" are points (B*N of them, point-major storage [rows, channels]).
+ *     A "group" is one cloud: rows_per_group consecutive rows.
+ *   - dtype codes: PCADV_F32 / PCADV_F16 / PCADV_BF16.  engine codes:
+ *     PCADV_ENGINE_SIMT = fp32 FFMA CUDA-core kernels (the fp32-accumulate
+ *     verification mode and the small / unaligned layers), PCADV_ENGINE_TC =
+ *     tcgen05 + TMEM + TMA kernels (16-bit operands, fp32 accumulate).
+ */
+#ifndef PCADV_H_
+#define PCADV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCADV_VERSION 100
+
+enum { PCADV_F32 = 0, PCADV_F16 = 1, PCADV_BF16 = 2, PCADV_I32 = 3, PCADV_I64 = 4 };
+enum { PCADV_ACT_NONE = 0, PCADV_ACT_RELU = 1, PCADV_ACT_LEAKY = 2 };
+enum { PCADV_ENGINE_SIMT = 0, PCADV_ENGINE_TC = 1 };
+#define PCADV_MAX_SEG 6
+
+/* One K-segment of the left operand: a [rows, k] row-major matrix with leading
+ * dimension `ld` (elements).  Several segments stand for the channel concat of
+ * models/pointnet.py:306 (torch.cat of x1..x5) without materialising it. */
+typedef struct pcadv_seg {
+  const void* ptr;
+  int64_t ld;
+  int32_t k;
+  int32_t dtype;
+} pcadv_seg;
+
+/*
+ * pcadv_linear: out[r, c] = post( sum_seg sum_k seg[r, k] * w[c, koff_seg + k]
+ *                                  + bias[c] + group_bias[r / rows_per_group, c]
+ *                                  + addend[r, c] )
+ *   post(v) = act(v) * act'(mask[r, c]) * (*out_scale)
+ * Replaces: Conv1d(k=1) + F.relu        models/pointnet.py:115-128, :291-301
+ *           nn.Linear on B x N x C      models/pointnet.py:309-314
+ *           the discriminator convs     models/discriminator.py:22-24, :44-48, :64-67
+ *           their dgrad in autograd (mask = the forward layer's saved output).
+ *   group_bias carries the folded global-feature / class-one-hot part of the
+ *   3024-wide concat (models/pointnet.py:304-309), one row per cloud.
+ * Optional fused reductions (out may be NULL when only these are wanted):
+ *   colmax_key[g, c] : packed (value, first index) max over the rows of cloud g
+ *                      of the PRE-activation value -- torch.max(x, 2) at
+ *                      models/pointnet.py:31, :64, :129, :303; unpack with
+ *                      pcadv_max_finalize.  Must be zero-filled by the caller.
+ *   rowmax_key[r]    : same over the columns of row r -- torch.max over channels
+ *                      at models/discriminator.py:71, :135, :169.
+ */
+typedef struct pcadv_linear_args {
+  int64_t rows;
+  int32_t n;
+  int32_t num_seg;
+  pcadv_seg seg[PCADV_MAX_SEG];
+  const void* w;              /* [n, ktot] row-major, ktot = sum seg[i].k */
+  int64_t ldw;
+  int32_t w_dtype;
+  int32_t engine;
+  const float* bias;          /* [n] or NULL */
+  const float* group_bias;    /* [rows / rows_per_group, n] or NULL */
+  int64_t rows_per_group;     /* required with group_bias / colmax_key */
+  const float* addend;        /* fp32 [rows, n] or NULL */
+  int64_t ld_addend;
+  int32_t act;
+  float slope;
+  const void* mask;           /* saved forward activation [rows, n] or NULL */
+  int64_t ld_mask;
+  int32_t mask_dtype;
+  int32_t mask_act;
+  float mask_slope;
+  int32_t out_dtype;
+  const float* out_scale;     /* device scalar or NULL */
+  void* out;                  /* [rows, n] or NULL */
+  int64_t ld_out;
+  unsigned long long* colmax_key;
+  unsigned long long* rowmax_key;
+} pcadv_linear_args;
+
+int pcadv_linear(const pcadv_linear_args* a, void* stream);
+
+/*
+ * pcadv_wgrad: dw[c, koff_seg + k] += scale * sum_r dz[r, c] * seg[r, k]
+ *              dbias[c]            += scale * sum_r dz[r, c]
+ *              dgroup_bias[g, c]   += sum_{r in cloud g} dz[r, c]   (NOT scaled)
+ * Replaces the weight / bias gradients autograd derives for the layers above.
+ * Outputs are fp32 and are accumulated into (caller zero-fills).
+ */
+typedef struct pcadv_wgrad_args {
+  int64_t rows;
+  int32_t n;
+  int32_t num_seg;
+  const void* dz;             /* [rows, n] */
+  int64_t ld_dz;
+  int32_t dz_dtype;
+  int32_t engine;
+  pcadv_seg seg[PCADV_MAX_SEG];
+  float* dw;                  /* [n, ktot] or NULL */
+  int64_t ld_dw;
+  float* dbias;               /* [n] or NULL */
+  float* dgroup_bias;         /* [rows / rows_per_group, n] or NULL */
+  int64_t rows_per_group;
+  const float* scale;         /* device scalar or NULL */
+} pcadv_wgrad_args;
+
+int pcadv_wgrad(const pcadv_wgrad_args* a, void* stream);
+
+/* Unpack `count` packed max keys: val = act(value), idx = first index (0 when a
+ * ReLU layer's maximum is <= 0, as every post-ReLU value then ties at 0 and
+ * torch.max returns the first).  idx may be NULL. */
+int pcadv_max_finalize(const unsigned long long* key, int64_t count, int32_t act, float slope,
+                       float* val, int32_t* idx, void* stream);
+
+/*
+ * pcadv_maxpool_bwd: backward of "layer + activation + max over the cloud's
+ * points" (models/pointnet.py:301-303) through the saved argmax only.
+ *   dzc = dg[g, c] * act'(gval[g, c]);  r = g * rows_per_group + idx[g, c]
+ *   dw[c, :]    += scale * dzc * x[r, :]
+ *   dbias[c]    += scale * dzc
+ *   dx_acc[r,:] += dzc * w[c, :]                (fp32 scatter-add, NOT scaled)
+ * Replaces the dense B x C x N scatter + dgrad + wgrad autograd runs.
+ */
+typedef struct pcadv_maxbwd_args {
+  int32_t groups;
+  int32_t n;                  /* channels of the pooled layer */
+  int32_t k;                  /* its input channels */
+  int32_t act;
+  float slope;
+  int32_t x_dtype;
+  int32_t w_dtype;
+  int32_t reserved;
+  int64_t rows_per_group;
+  const float* dg;            /* [groups, n] */
+  const float* gval;          /* [groups, n] pooled post-activation value */
+  const int32_t* idx;         /* [groups, n] */
+  const void* x;              /* [groups * rows_per_group, k] */
+  int64_t ldx;
+  const void* w;              /* [n, k] */
+  int64_t ldw;
+  float* dw;                  /* [n, k] or NULL */
+  int64_t ld_dw;
+  float* dbias;               /* [n] or NULL */
+  float* dx_acc;              /* [rows, k] fp32 or NULL */
+  int64_t ld_dx;
+  const float* scale;
+} pcadv_maxbwd_args;
+
+int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream);
+
+/* Backward of the max over channels: dz[r, c] = (c == idx[r]) ? dy[r] * (*scale) *
+ * act'(val[r]) : 0, written densely as `dz_dtype`. */
+int pcadv_rowmax_bwd(const float* dy, const float* val, const int32_t* idx, int64_t rows, int32_t n,
+                     int32_t act, float slope, const float* scale, void* dz, int64_t ld_dz,
+                     int32_t dz_dtype, void* stream);
+
+/* scale2[0] = S = 2^floor(log2(target / max|x|)) (1 when x is all zero),
+ * scale2[1] = 1 / S.  x is a [rows, cols] fp32 matrix with leading dimension ld.
+ * `workspace` is one zero-filled uint32. */
+int pcadv_amax_scale(const float* x, int64_t rows, int32_t cols, int64_t ld, float target,
+                     unsigned int* workspace, float* scale2, void* stream);
+
+/* dst[r, c] = convert(src[r, c] * (*scale) * act'(mask[r, c])) for c < cols, 0 for
+ * cols <= c < cols_pad.  scale and mask are optional (NULL). */
+int pcadv_convert(const void* src, int32_t src_dtype, int64_t ld_src, int64_t rows, int32_t cols,
+                  void* dst, int32_t dst_dtype, int64_t ld_dst, int32_t cols_pad, const float* scale,
+                  const void* mask, int64_t ld_mask, int32_t mask_dtype, int32_t mask_act,
+                  float mask_slope, void* stream);
+
+/* dst[c, r] = src[r, c] with conversion: builds the [k, n] copy of a weight
+ * matrix that dgrad consumes. */
+int pcadv_transpose(const void* src, int32_t src_dtype, int64_t ld_src, int32_t rows, int32_t cols,
+                    void* dst, int32_t dst_dtype, int64_t ld_dst, void* stream);
+
+int pcadv_version(void);
+/* 0 when the current device is compute capability 10.x, else non-zero. */
+int pcadv_device_check(void);
+const char* pcadv_last_error(void);
+/* Number of kernel launches issued by this library since process start. */
+long long pcadv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PCADV_H_ */
