@@ -27,7 +27,7 @@ class Layer:
 def compute_weight(prec, w32, k_list, n):
     """The copy of a weight matrix the engine multiplies with: a 16-bit copy when
     the tensor-core engine can take the shape, else the fp32 master."""
-    if prec.engine == ENGINE_TC and all(k % 64 == 0 for k in k_list) and n % 16 == 0:
+    if prec.engine == ENGINE_TC and all(k % 64 == 0 for k in k_list):
         return w32.to(prec.act_dtype)
     return w32
 
@@ -49,12 +49,12 @@ def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, grou
     return ys
 
 
-def pad_cols(t, mult=64):
-    """Zero-pad the column count of a small weight matrix to a multiple of ``mult``."""
+def pad_cols(t, width):
+    """Zero-pad the columns of a small weight matrix to ``width``."""
     n = t.shape[1]
-    if n % mult == 0:
+    if n == width:
         return t
-    out = t.new_zeros((t.shape[0], (n + mult - 1) // mult * mult))
+    out = t.new_zeros((t.shape[0], width))
     out[:, :n] = t
     return out
 
@@ -75,17 +75,17 @@ def prepare_dz(prec, dy, scale2, mask=None, mask_act=ACT_NONE, mask_slope=0.0):
                        mask=mask, mask_act=mask_act, mask_slope=mask_slope)
 
 
-def dgrad_weight(prec, blocks, n_out):
+def dgrad_weight(prec, blocks, n_out, widths):
     """Weight of a dgrad GEMM: the K-concat of transposed forward weights.
-    ``blocks`` = list of [Cout_i, n_out] forward-weight slices (fp32); the result
-    is [n_out, sum(pad64(Cout_i))] in the compute dtype."""
+    ``blocks`` = list of [Cout_i, n_out] forward-weight slices (fp32), ``widths`` the
+    column counts of the dz matrices they multiply (>= Cout_i when dz carries
+    zero padding); the result is [n_out, sum(widths)] in the compute dtype."""
     parts = []
-    for wb in blocks:
-        t = wb.t()
-        parts.append(pad_cols(t) if prec.scaled else t)
+    for wb, width in zip(blocks, widths):
+        parts.append(pad_cols(wb.t(), width))
     wt = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
     wt = wt.contiguous()
-    if prec.engine == ENGINE_TC and n_out % 16 == 0 and wt.shape[1] % 64 == 0:
+    if prec.engine == ENGINE_TC and wt.shape[1] % 64 == 0:
         return wt.to(prec.act_dtype)
     return wt
 
@@ -123,14 +123,14 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
         if i == 0:
             break
         P = layers[i - 1]
-        wt = dgrad_weight(prec, [L.w], L.w.shape[1])
+        wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz.shape[1]])
         dz, _, _ = ops.linear([dz], wt, mask=ys[i - 1], mask_act=P.act, mask_slope=P.slope,
                               out_dtype=prec.act_dtype, engine=prec.engine,
                               addend=addends.get(i - 1))
     dx = None
     if need_x:
         L = layers[0]
-        wt = dgrad_weight(prec, [L.w], L.w.shape[1])
+        wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz.shape[1]])
         inv = scale2[1:2] if scale2 is not None else None
         dx, _, _ = ops.linear([dz], wt, out_dtype=torch.float32, out_scale=inv, engine=prec.engine)
     return grads, dx, dz

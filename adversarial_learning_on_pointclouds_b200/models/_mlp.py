@@ -134,7 +134,7 @@ class PointMLPFunction(torch.autograd.Function):
                                         slope=L.slope, scale=S, out_dtype=prec.act_dtype)
                 grads[-1] = layer_wgrad(prec, dz_red, [src], L.w.shape, need_w[-1], need_b[-1], scale2)
                 if body or need_x:
-                    wt = dgrad_weight(prec, [L.w], L.w.shape[1])
+                    wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz_red.shape[1]])
                     if body:
                         P_ = body[-1]
                         dz_last, _, _ = ops.linear([dz_red], wt, mask=src, mask_act=P_.act,

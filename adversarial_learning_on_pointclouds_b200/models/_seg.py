@@ -93,7 +93,7 @@ class SegFunction(torch.autograd.Function):
             dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
                                  need[name + ".bias"], scale2)
             grads[name + ".weight"], grads[name + ".bias"] = dw, db
-            wt = dgrad_weight(prec, [W[name]], W[name].shape[1])
+            wt = dgrad_weight(prec, [W[name]], W[name].shape[1], [dz.shape[1]])
             dz, _, _ = ops.linear([dz], wt, mask=xin, mask_act=ACT_RELU, out_dtype=prec.act_dtype,
                                   engine=prec.engine)
         dz_fc1 = dz                                                   # [P, 256], scaled
@@ -124,7 +124,7 @@ class SegFunction(torch.autograd.Function):
 
         # ---- trunk: dz_k = relu'(x_k) * ([dz_{k+1} | dz_fc1] @ [W_{k+1}; fc1.W[:, slice_k]]) --
         s5 = _SLICES[4]
-        wt = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512)
+        wt = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512, [256])
         dz, _, _ = ops.linear([dz_fc1], wt, addend=dx5_sparse, mask=xs[4], mask_act=ACT_RELU,
                               out_dtype=prec.act_dtype, engine=prec.engine)
         del dx5_sparse
@@ -135,7 +135,8 @@ class SegFunction(torch.autograd.Function):
                                  need[name + ".bias"], scale2)
             grads[name + ".weight"], grads[name + ".bias"] = dw, db
             sl = _SLICES[li - 1]
-            wt = dgrad_weight(prec, [W[name], W["fc1"][:, sl[0]:sl[1]]], W[name].shape[1])
+            wt = dgrad_weight(prec, [W[name], W["fc1"][:, sl[0]:sl[1]]], W[name].shape[1],
+                              [dz.shape[1], 256])
             dz, _, _ = ops.linear([dz, dz_fc1], wt, mask=xin, mask_act=ACT_RELU,
                                   out_dtype=prec.act_dtype, engine=prec.engine)
         dw, db = layer_wgrad(prec, dz, [pts2], W["conv1"].shape, need["conv1.weight"],

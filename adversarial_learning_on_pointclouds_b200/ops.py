@@ -86,7 +86,7 @@ def tc_eligible(segs, w, n):
             return False
     if w.dtype != segs[0].dtype or w.stride(0) % 8 or w.data_ptr() % 16:
         return False
-    return n % 16 == 0 and segs[0].shape[0] >= 128
+    return segs[0].shape[0] >= 128
 
 
 def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None, act=ACT_NONE,

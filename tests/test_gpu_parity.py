@@ -393,7 +393,7 @@ def test_adversarial_step_vs_oracle_step(mode):
     assert abs(l_seg - ref["l_seg"]) < 10 * tol and abs(l_adv - ref["l_adv"]) < 10 * tol
     # unconditioned comparison: ReLU / argmax ties may move single entries, so the bound is
     # looser than the branch-conditioned one in test_seg_matches_oracle
-    loose = 50 * tol
+    loose = max(50 * tol, 5e-3)
     for k, v in d.named_parameters():
         assert rel_err(v.grad, dp[k].grad) < loose, k
     for k, v in g.named_parameters():

@@ -1,0 +1,93 @@
+"""GPU: the tensor-core engine (tcgen05 / TMEM / TMA kernels) against fp64 torch
+on the same 16-bit operands.  Operands are exactly representable in the storage
+dtype, so the only error is fp32 accumulation order: tolerance 1e-5 relative on
+the fp32 accumulator, 1e-3 after rounding to a 16-bit output."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from adversarial_learning_on_pointclouds_b200 import ops
+from adversarial_learning_on_pointclouds_b200.ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, ENGINE_TC)
+from helpers import rel_err
+
+DEV = "cuda"
+DT = [torch.float16, torch.bfloat16]
+
+
+def _rand(shape, seed, dtype, scale=1.0):
+    return (torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale).to(DEV).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,ks,n", [(128, [64], 64), (1000, [64], 128), (5000, [128], 256),
+                                       (4096, [128], 512), (3000, [64, 128, 128, 128, 512], 256),
+                                       (2500, [128], 50), (777, [512, 256], 128), (300, [64], 16)])
+def test_tc_linear_plain(dtype, rows, ks, n):
+    segs = [_rand((rows, k), 10 + i, dtype) for i, k in enumerate(ks)]
+    w = _rand((n, sum(ks)), 3, dtype, 0.1)
+    out, _, _ = ops.linear(segs, w, out_dtype=torch.float32, engine=ENGINE_TC)
+    ref = torch.cat(segs, 1).double() @ w.double().t()
+    err = rel_err(out, ref)
+    print(dtype, rows, ks, n, "rel err", err)
+    assert err < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_tc_linear_full_epilogue(dtype):
+    rows, ks, n, rpg = 5000, [64, 128], 256, 2500
+    segs = [_rand((rows, k), 10 + i, dtype) for i, k in enumerate(ks)]
+    w = _rand((n, sum(ks)), 3, dtype, 0.1)
+    bias = _rand((n,), 4, torch.float32)
+    gb = _rand((rows // rpg, n), 5, torch.float32)
+    add = _rand((rows, n), 6, torch.float32)
+    mask = _rand((rows, n), 7, dtype)
+    sc = torch.tensor([0.5], device=DEV)
+    out, _, rkey = ops.linear(segs, w, bias=bias, group_bias=gb, rows_per_group=rpg, addend=add,
+                              act=ACT_LEAKY, slope=0.2, mask=mask, mask_act=ACT_RELU, out_scale=sc,
+                              out_dtype=dtype, rowmax=True, engine=ENGINE_TC)
+    pre = torch.cat(segs, 1).double() @ w.double().t() + bias.double() + \
+        gb.double().repeat_interleave(rpg, 0) + add.double()
+    ref = F.leaky_relu(pre, 0.2) * (mask > 0) * 0.5
+    assert out.dtype == dtype
+    assert rel_err(out, ref) < (1e-3 if dtype == torch.float16 else 6e-3)
+    rval, ridx = ops.max_finalize(rkey, ACT_RELU)
+    rv, ri = F.relu(pre).max(1)
+    assert rel_err(rval, rv) < 1e-5
+    assert ((ridx.long() == ri) | (rv == 0)).double().mean().item() > 0.995
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,N,k,n", [(3, 500, 128, 256), (2, 2500, 512, 2048), (5, 100, 64, 1024),
+                                     (1, 4096, 128, 512)])
+def test_tc_colmax_over_points(dtype, B, N, k, n):
+    x = _rand((B * N, k), 1, dtype)
+    w = _rand((n, k), 2, dtype, 0.1)
+    b = _rand((n,), 3, torch.float32)
+    _, key, _ = ops.linear([x], w, bias=b, want_out=False, colmax=True, rows_per_group=N,
+                           engine=ENGINE_TC)
+    g, idx = ops.max_finalize(key, ACT_RELU)
+    y = F.relu(x.double() @ w.double().t() + b.double()).view(B, N, n)
+    gv, gi = y.max(1)
+    assert rel_err(g, gv) < 1e-5
+    at = torch.gather(y, 1, idx.long().unsqueeze(1)).squeeze(1)
+    assert ((gv - at).abs() <= 1e-5 * gv.abs().clamp_min(1e-3)).all()      # argmax within rounding
+    assert ((idx.long() == gi) | (gv == 0)).double().mean().item() > 0.99
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,ks,n", [(1000, [64], 64), (5000, [128], 256), (40000, [128], 512),
+                                       (3000, [64, 128, 128, 128, 512], 256), (2500, [128], 64),
+                                       (100000, [512], 128)])
+def test_tc_wgrad(dtype, rows, ks, n):
+    dz = _rand((rows, n), 1, dtype)
+    segs = [_rand((rows, k), 10 + i, dtype) for i, k in enumerate(ks)]
+    sc = torch.tensor([0.5], device=DEV)
+    dw = torch.zeros((n, sum(ks)), device=DEV)
+    db = torch.zeros((n,), device=DEV)
+    ops.wgrad(dz, segs, dw=dw, dbias=db, scale=sc, engine=ENGINE_TC)
+    x = torch.cat(segs, 1).double()
+    e1, e2 = rel_err(dw, 0.5 * dz.double().t() @ x), rel_err(db, 0.5 * dz.double().sum(0))
+    print(dtype, rows, ks, n, "dw", e1, "db", e2)
+    assert e1 < 1e-5 and e2 < 1e-5
