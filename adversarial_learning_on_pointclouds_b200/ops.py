@@ -48,6 +48,47 @@ def default_precision():
     return _DEFAULT[0]
 
 
+class KernelTimer:
+    """Context manager that brackets every libpcadv call made inside it with CUDA
+    events on the current stream (the stream the kernels are launched on) and
+    keeps them per call signature, e.g. ``linear:tc:k512:n2048:colmax``.
+    ``summary()`` synchronises and returns {signature: (calls, total_ms)}."""
+
+    def __init__(self):
+        self.records = {}
+
+    def __enter__(self):
+        global _TIMER
+        self._prev, _TIMER = _TIMER, self
+        return self
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = self._prev
+
+    def add(self, tag, start, end):
+        self.records.setdefault(tag, []).append((start, end))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {tag: (len(ev), sum(a.elapsed_time(b) for a, b in ev)) for tag, ev in self.records.items()}
+
+
+_TIMER = None
+
+
+def _call(tag, fn, *args):
+    timer = _TIMER
+    if timer is None:
+        _lib.check(fn(*args))
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    _lib.check(fn(*args))
+    end.record()
+    timer.add(tag, start, end)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -142,7 +183,11 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
     if rowmax:
         rkey = torch.zeros((rows,), dtype=torch.int64, device=dev)
         a.rowmax_key = C.c_void_p(rkey.data_ptr())
-    _lib.check(_lib.lib().pcadv_linear(C.byref(a), _stream()))
+    tag = "linear:%s:k%d:n%d%s%s%s%s" % ("tc" if engine == ENGINE_TC else "simt", ktot, n,
+                                       ":colmax" if colmax else "", ":rowmax" if rowmax else "",
+                                       ":mask" if mask is not None else "",
+                                       ":addend" if addend is not None else "")
+    _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream())
     return out, ckey, rkey
 
 
@@ -179,15 +224,18 @@ def wgrad(dz, segs, *, dw=None, dbias=None, dgroup_bias=None, rows_per_group=0, 
         if not ok:
             engine = ENGINE_SIMT
     a.engine = engine
-    _lib.check(_lib.lib().pcadv_wgrad(C.byref(a), _stream()))
+    tag = "wgrad:%s:n%d:k%d%s%s" % ("tc" if engine == ENGINE_TC else "simt", n, ktot,
+                                    ":dbias" if dbias is not None else "",
+                                    ":dgroup" if dgroup_bias is not None else "")
+    _call(tag, _lib.lib().pcadv_wgrad, C.byref(a), _stream())
 
 
 def max_finalize(key, act=ACT_NONE, slope=0.0, want_idx=True):
     """Unpack packed max keys -> (val fp32, idx int32) with the shape of ``key``."""
     val = torch.empty(key.shape, dtype=torch.float32, device=key.device)
     idx = torch.empty(key.shape, dtype=torch.int32, device=key.device) if want_idx else None
-    _lib.check(_lib.lib().pcadv_max_finalize(_ptr(key), key.numel(), act, float(slope), _ptr(val),
-                                             _ptr(idx), _stream()))
+    _call("max_finalize", _lib.lib().pcadv_max_finalize, _ptr(key), key.numel(), act, float(slope),
+          _ptr(val), _ptr(idx), _stream())
     return val, idx
 
 
@@ -215,15 +263,15 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
             raise ValueError("dx_acc must be fp32")
         a.dx_acc, a.ld_dx = p, ld
     a.scale = _f32(scale) if scale is not None else None
-    _lib.check(_lib.lib().pcadv_maxpool_bwd(C.byref(a), _stream()))
+    _call("maxpool_bwd:n%d:k%d" % (n, a.k), _lib.lib().pcadv_maxpool_bwd, C.byref(a), _stream())
 
 
 def rowmax_bwd(dy, val, idx, n, *, act=ACT_NONE, slope=0.0, scale=None, out_dtype=torch.float32):
     rows = dy.numel()
     dz = torch.empty((rows, n), dtype=out_dtype, device=dy.device)
-    _lib.check(_lib.lib().pcadv_rowmax_bwd(_f32(dy), _f32(val), _ptr(idx), rows, n, act, float(slope),
-                                           _f32(scale) if scale is not None else None, _ptr(dz), n,
-                                           _DT[out_dtype], _stream()))
+    _call("rowmax_bwd:n%d" % n, _lib.lib().pcadv_rowmax_bwd, _f32(dy), _f32(val), _ptr(idx), rows, n,
+          act, float(slope), _f32(scale) if scale is not None else None, _ptr(dz), n, _DT[out_dtype],
+          _stream())
     return dz
 
 
@@ -239,8 +287,8 @@ def amax_scale(xs, target=256.0):
         p, ld, dt = _mat(x)
         if dt != F32:
             raise ValueError("amax_scale expects fp32")
-        _lib.check(_lib.lib().pcadv_amax_scale(p, x.shape[0], x.shape[1], ld, float(target), _ptr(ws),
-                                               _ptr(s2), _stream()))
+        _call("amax_scale", _lib.lib().pcadv_amax_scale, p, x.shape[0], x.shape[1], ld, float(target),
+              _ptr(ws), _ptr(s2), _stream())
     return s2
 
 
@@ -251,9 +299,9 @@ def convert(src, out_dtype, cols_pad=None, scale=None, mask=None, mask_act=ACT_N
     cols_pad = int(cols_pad or cols)
     dst = torch.empty((rows, cols_pad), dtype=out_dtype, device=src.device)
     mp, mld, mdt = _mat(mask) if mask is not None else (C.c_void_p(0), 0, F32)
-    _lib.check(_lib.lib().pcadv_convert(p, dt, ld, rows, cols, _ptr(dst), _DT[out_dtype], cols_pad,
-                                        cols_pad, _f32(scale) if scale is not None else None,
-                                        mp, mld, mdt, mask_act, float(mask_slope), _stream()))
+    _call("convert:c%d" % cols_pad, _lib.lib().pcadv_convert, p, dt, ld, rows, cols, _ptr(dst),
+          _DT[out_dtype], cols_pad, cols_pad, _f32(scale) if scale is not None else None, mp, mld, mdt,
+          mask_act, float(mask_slope), _stream())
     return dst
 
 
@@ -268,6 +316,6 @@ def transpose(src, out_dtype=None):
     return dst
 
 
-__all__ = ["Precision", "set_default_precision", "default_precision", "linear", "wgrad",
+__all__ = ["KernelTimer", "Precision", "set_default_precision", "default_precision", "linear", "wgrad",
            "max_finalize", "maxpool_bwd", "rowmax_bwd", "amax_scale", "convert", "transpose",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ENGINE_SIMT", "ENGINE_TC"]
