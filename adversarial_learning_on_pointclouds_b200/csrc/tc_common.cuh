@@ -44,6 +44,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Single-thread role loops (TMA producer, MMA issuer) wait with a suspend-time hint so the
+// spinning lane does not steal issue slots from the epilogue warps of its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(2000u)
+        : "memory");
+  }
+}
+
 // ---- TMA ----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -56,6 +74,33 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
       "r"(c1)
       : "memory");
+}
+
+// smem tile -> global through the tensor map (clips to the tensor extent); bulk-group tracked
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
+                                             int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+// make generic-proxy smem writes visible to the async proxy (TMA) before a bulk store
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---- TMEM -----------------------------------------------------------------------------
@@ -137,6 +182,11 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool bf16,
 // box = box_cols x box_rows elements, 128-byte swizzle (box_cols must be 64).
 int encode_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int64_t cols,
                    int64_t ld, int box_cols, int box_rows);
+// true when a [rows, cols] matrix of `dtype` with leading dimension ld can be a TMA tensor
+inline bool tma_compatible(const void* base, int dtype, int64_t ld) {
+  const int esz = dtype == PCADV_F32 ? 4 : 2;
+  return base != nullptr && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * esz) % 16 == 0;
+}
 
 }  // namespace tc
 }  // namespace pcadv

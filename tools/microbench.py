@@ -1,0 +1,129 @@
+#!/usr/bin/env python3
+"""Micro-benchmark of single libpcadv ops at the cfg5 shapes (rows = 2^20 points),
+timed with CUDA events on the launching stream after warm-up.  Prints achieved
+GB/s (algorithmic bytes) and TFLOP/s per op.  ``--only NAME`` runs one case (for
+an ncu capture: ``ncu --set full -k regex:tc_linear ... python tools/microbench.py
+--only conv5 --iters 1``)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from adversarial_learning_on_pointclouds_b200 import ops
+from adversarial_learning_on_pointclouds_b200.ops import ACT_RELU, ENGINE_TC, ENGINE_SIMT
+
+DEV = "cuda"
+
+
+def r16(shape, scale=1.0):
+    return (torch.randn(shape, device=DEV) * scale).half()
+
+
+def cases(P, N):
+    B = P // N
+    c = {}
+
+    def lin(name, ks, n, out_dtype=torch.float16, mask=False, addend=False, bias=True, colmax=False,
+            rowmax=False, want_out=True, gb=False):
+        segs = [r16((P, k)) for k in ks]
+        w = r16((n, sum(ks)), 0.05)
+        kw = dict(bias=torch.randn(n, device=DEV) if bias else None, act=ACT_RELU, out_dtype=out_dtype,
+                  engine=ENGINE_TC, colmax=colmax, rowmax=rowmax, want_out=want_out,
+                  rows_per_group=N if (colmax or gb) else 0)
+        if mask:
+            kw.update(mask=r16((P, n)), mask_act=ACT_RELU)
+        if addend:
+            kw.update(addend=torch.randn((P, n), device=DEV))
+        if gb:
+            kw.update(group_bias=torch.randn((B, n), device=DEV))
+        esz = 2 if out_dtype == torch.float16 else 4
+        nbytes = P * (2 * sum(ks) + (esz * n if want_out else 0) + (2 * n if mask else 0) +
+                      (4 * n if addend else 0))
+        flops = 2.0 * P * sum(ks) * n
+        c[name] = (lambda: ops.linear(segs, w, **kw), nbytes, flops)
+
+    lin("conv2", [64], 128)
+    lin("conv3", [128], 128)
+    lin("conv5", [128], 512)
+    lin("conv6max", [512], 2048, colmax=True, want_out=False)
+    lin("fc1", [64, 128, 128, 128, 512], 256, gb=True, bias=False)
+    lin("fc2", [256], 256)
+    lin("fc3", [256], 128)
+    lin("fc4", [128], 50, out_dtype=torch.float32)
+    lin("dz_fc3", [64], 128, mask=True, bias=False)
+    lin("dz_fc2", [128], 256, mask=True, bias=False)
+    lin("dz_fc1", [256], 256, mask=True, bias=False)
+    lin("dz5", [256], 512, mask=True, addend=True, bias=False)
+    lin("dz4", [512, 256], 128, mask=True, bias=False)
+    lin("dz3", [128, 256], 128, mask=True, bias=False)
+    lin("dz1", [128, 256], 64, mask=True, bias=False)
+    lin("disc4max", [64], 128, rowmax=True, want_out=False)
+
+    def wg(name, n, ks, dbias=True):
+        dz = r16((P, n))
+        segs = [r16((P, k)) for k in ks]
+        dw = torch.zeros((n, sum(ks)), device=DEV)
+        db = torch.zeros((n,), device=DEV) if dbias else None
+        nbytes = P * 2 * (n + sum(ks))
+        c[name] = (lambda: ops.wgrad(dz, segs, dw=dw, dbias=db, engine=ENGINE_TC), nbytes,
+                   2.0 * P * n * sum(ks))
+
+    wg("wg_fc1", 256, [64, 128, 128, 128, 512], dbias=False)
+    wg("wg_conv5", 512, [128])
+    wg("wg_fc2", 256, [256])
+    wg("wg_conv3", 128, [128])
+    wg("wg_d2", 64, [64])
+
+    x50 = torch.randn((P, 50), device=DEV)
+    w50 = torch.randn((64, 50), device=DEV) * 0.1
+    c["disc1_simt"] = (lambda: ops.linear([x50], w50, bias=torch.zeros(64, device=DEV), act=ACT_RELU,
+                                          out_dtype=torch.float16, engine=ENGINE_SIMT),
+                       P * (200 + 128), 2.0 * P * 50 * 64)
+    pts = torch.randn((P, 3), device=DEV)
+    w3 = torch.randn((64, 3), device=DEV)
+    c["conv1_simt"] = (lambda: ops.linear([pts], w3, bias=torch.zeros(64, device=DEV), act=ACT_RELU,
+                                          out_dtype=torch.float16, engine=ENGINE_SIMT),
+                       P * (12 + 128), 2.0 * P * 3 * 64)
+    dy = torch.randn(P, device=DEV)
+    val = torch.rand(P, device=DEV)
+    idx = torch.randint(0, 128, (P,), device=DEV, dtype=torch.int32)
+    c["rowmax_bwd"] = (lambda: ops.rowmax_bwd(dy, val, idx, 128, act=ACT_RELU, out_dtype=torch.float16),
+                       P * (12 + 256), 0.0)
+    dl = torch.randn((P, 50), device=DEV) * 1e-6
+    c["amax"] = (lambda: ops.amax_scale(dl), P * 200, 0.0)
+    s2 = torch.ones(2, device=DEV)
+    c["convert50"] = (lambda: ops.convert(dl, torch.float16, cols_pad=64, scale=s2[0:1]), P * 328, 0.0)
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=1 << 20)
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    cs = cases(args.points, args.n)
+    print("%-12s %9s %9s %9s" % ("op", "ms", "GB/s", "TFLOP/s"))
+    for name, (fn, nbytes, flops) in cs.items():
+        if args.only and name != args.only:
+            continue
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        print("%-12s %9.3f %9.0f %9.1f" % (name, ms, nbytes / ms / 1e6, flops / ms / 1e9))
+
+
+if __name__ == "__main__":
+    main()
