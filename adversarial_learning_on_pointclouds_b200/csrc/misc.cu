@@ -70,6 +70,151 @@ __global__ void __launch_bounds__(256) maxbwd_dx_kernel(const pcadv_maxbwd_args 
     atomicAdd(dst + k, dz * ld_as_float(a.w, static_cast<int64_t>(c) * a.ldw + k, a.w_dtype));
 }
 
+// ---- fast sparse max-pool backward (k % 64 == 0, k <= 1024, rows_per_group <= 8192) -------
+// pair loads: lane owns elements 2*lane + 64*j
+__device__ __forceinline__ float2 ld_pair(const void* p, int64_t i, int dtype) {
+  if (dtype == PCADV_F32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p) + i);
+  if (dtype == PCADV_F16) return __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p) + i));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+}
+__device__ __forceinline__ void st_pair(void* p, int64_t i, int dtype, float2 v) {
+  if (dtype == PCADV_F32) {
+    *reinterpret_cast<float2*>(reinterpret_cast<float*>(p) + i) = v;
+  } else if (dtype == PCADV_F16) {
+    *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p) + i) =
+        __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+  } else {
+    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+constexpr int kMaxPairs = 16;     // k <= 1024
+
+// dW / dbias: one CTA per channel c, 8 warps stride over the clouds; no atomics.
+__global__ void __launch_bounds__(256) maxbwd_dw_fast_kernel(const pcadv_maxbwd_args a) {
+  __shared__ float red[8][1024];
+  __shared__ float bred[8];
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pairs = a.k >> 6;
+  float2 acc[kMaxPairs];
+#pragma unroll
+  for (int j = 0; j < kMaxPairs; ++j) acc[j] = make_float2(0.f, 0.f);
+  float bsum = 0.f;
+  for (int g = warp; g < a.groups; g += 8) {
+    const int64_t gc = static_cast<int64_t>(g) * a.n + c;
+    const float dz = a.dg[gc] * act_grad_from_output(a.gval[gc], a.act, a.slope);
+    if (dz == 0.f) continue;
+    bsum += dz;
+    if (a.dw) {
+      const int64_t r = static_cast<int64_t>(g) * a.rows_per_group + a.idx[gc];
+#pragma unroll
+      for (int j = 0; j < kMaxPairs; ++j) {
+        if (j < pairs) {
+          const float2 x = ld_pair(a.x, r * a.ldx + 2 * lane + 64 * j, a.x_dtype);
+          acc[j].x = fmaf(dz, x.x, acc[j].x);
+          acc[j].y = fmaf(dz, x.y, acc[j].y);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxPairs; ++j) {
+    if (j < pairs) {
+      red[warp][2 * lane + 64 * j] = acc[j].x;
+      red[warp][2 * lane + 64 * j + 1] = acc[j].y;
+    }
+  }
+  if (lane == 0) bred[warp] = bsum;
+  __syncthreads();
+  const float sc = a.scale ? *a.scale : 1.f;
+  if (a.dw) {
+    for (int k = threadIdx.x; k < a.k; k += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][k];
+      a.dw[static_cast<int64_t>(c) * a.ld_dw + k] += s * sc;
+    }
+  }
+  if (threadIdx.x == 0 && a.dbias) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += bred[w];
+    a.dbias[c] += s * sc;
+  }
+}
+
+// dz of the previous layer: one CTA per cloud.  Channels are bucketed by their argmax row
+// in shared memory (count, scan, fill); each warp then sums one touched row in fp32 and
+// adds it once into dz_inout through the previous layer's activation mask.
+__global__ void __launch_bounds__(256) maxbwd_rows_kernel(const pcadv_maxbwd_args a) {
+  extern __shared__ int sm_i[];
+  int* ends = sm_i;                                        // [rows_per_group]
+  int* list = sm_i + a.rows_per_group;                     // [n] channels ordered by row
+  float* dzv = reinterpret_cast<float*>(list + a.n);       // [n]
+  __shared__ int part[256];
+  const int g = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int N = static_cast<int>(a.rows_per_group);
+  for (int r = t; r < N; r += 256) ends[r] = 0;
+  __syncthreads();
+  for (int c = t; c < a.n; c += 256) {
+    const int64_t gc = static_cast<int64_t>(g) * a.n + c;
+    const float dz = a.dg[gc] * act_grad_from_output(a.gval[gc], a.act, a.slope);
+    dzv[c] = dz;
+    if (dz != 0.f) atomicAdd(&ends[a.idx[gc]], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the counts: thread t owns a contiguous chunk of rows
+  const int chunk = (N + 255) / 256;
+  const int lo = t * chunk, hi = lo + chunk < N ? lo + chunk : N;
+  int s = 0;
+  for (int r = lo; r < hi; ++r) s += ends[r];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; }
+  }
+  __syncthreads();
+  int run = part[t];
+  for (int r = lo; r < hi; ++r) { const int v = ends[r]; ends[r] = run; run += v; }
+  __syncthreads();
+  // fill: ends[r] walks from the row's start to its end
+  for (int c = t; c < a.n; c += 256)
+    if (dzv[c] != 0.f) list[atomicAdd(&ends[a.idx[static_cast<int64_t>(g) * a.n + c]], 1)] = c;
+  __syncthreads();
+  const int pairs = a.k >> 6;
+  for (int r = warp; r < N; r += 8) {
+    const int beg = r == 0 ? 0 : ends[r - 1], end = ends[r];
+    if (beg == end) continue;
+    float2 acc[kMaxPairs];
+#pragma unroll
+    for (int j = 0; j < kMaxPairs; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int q = beg; q < end; ++q) {
+      const int c = list[q];
+      const float dz = dzv[c];
+#pragma unroll
+      for (int j = 0; j < kMaxPairs; ++j) {
+        if (j < pairs) {
+          const float2 w = ld_pair(a.w, static_cast<int64_t>(c) * a.ldw + 2 * lane + 64 * j, a.w_dtype);
+          acc[j].x = fmaf(dz, w.x, acc[j].x);
+          acc[j].y = fmaf(dz, w.y, acc[j].y);
+        }
+      }
+    }
+    const int64_t row = static_cast<int64_t>(g) * a.rows_per_group + r;
+#pragma unroll
+    for (int j = 0; j < kMaxPairs; ++j) {
+      if (j < pairs) {
+        const int64_t kk = 2 * lane + 64 * j;
+        const float2 x = ld_pair(a.x, row * a.ldx + kk, a.x_dtype);
+        float2 d = ld_pair(a.dz_inout, row * a.ld_dz + kk, a.dz_dtype);
+        d.x += acc[j].x * act_grad_from_output(x.x, a.prev_act, a.prev_slope);
+        d.y += acc[j].y * act_grad_from_output(x.y, a.prev_act, a.prev_slope);
+        st_pair(a.dz_inout, row * a.ld_dz + kk, a.dz_dtype, d);
+      }
+    }
+  }
+}
+
 __global__ void rowmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ val,
                                   const int32_t* __restrict__ idx, int64_t rows, int n, int act,
                                   float slope, const float* scale, void* dz, int64_t ld_dz,
@@ -172,9 +317,30 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
   PCADV_CHECK_ARG(a->groups > 0 && a->n > 0 && a->k > 0 && a->rows_per_group > 0,
                   "pcadv_maxpool_bwd: bad shape");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto pair_ok = [](const void* p, int64_t ld, int dtype) {
+    return p == nullptr || (ld % 2 == 0 && (reinterpret_cast<uintptr_t>(p) & (dtype == PCADV_F32 ? 7 : 3)) == 0);
+  };
+  const bool fast = a->k % 64 == 0 && a->k <= 64 * kMaxPairs && pair_ok(a->x, a->ldx, a->x_dtype) &&
+                    pair_ok(a->w, a->ldw, a->w_dtype) && pair_ok(a->dz_inout, a->ld_dz, a->dz_dtype);
   if (a->dw || a->dbias) {
     PCADV_CHECK_ARG(!a->dw || a->x, "pcadv_maxpool_bwd: dw needs x");
-    maxbwd_dw_kernel<<<a->n, 128, 0, s>>>(*a);
+    if (fast) maxbwd_dw_fast_kernel<<<a->n, 256, 0, s>>>(*a);
+    else maxbwd_dw_kernel<<<a->n, 128, 0, s>>>(*a);
+    PCADV_LAUNCHED();
+  }
+  if (a->dz_inout) {
+    PCADV_CHECK_ARG(a->w && a->x, "pcadv_maxpool_bwd: dz_inout needs w and x");
+    PCADV_CHECK_ARG(fast && a->rows_per_group <= 8192 && a->n <= 4096,
+                    "pcadv_maxpool_bwd: dz_inout needs k %% 64 == 0, k <= 1024, rows_per_group <= 8192, "
+                    "n <= 4096 (got k=%d rpg=%lld n=%d)", a->k, (long long)a->rows_per_group, a->n);
+    const size_t smem = (static_cast<size_t>(a->rows_per_group) + 2 * static_cast<size_t>(a->n)) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+      PCADV_CUDA_OK(cudaFuncSetAttribute(maxbwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (8192 + 2 * 4096) * 4));
+      attr_done = true;
+    }
+    maxbwd_rows_kernel<<<a->groups, 256, smem, s>>>(*a);
     PCADV_LAUNCHED();
   }
   if (a->dx_acc) {

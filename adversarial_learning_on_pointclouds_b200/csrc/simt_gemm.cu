@@ -314,9 +314,88 @@ __global__ void __launch_bounds__(256) group_colsum_kernel(const void* dz, int d
   }
 }
 
+// =====================================================================================
+// First layer (K <= 4, e.g. Conv1d(3, 64, 1) at models/pointnet.py:115, :291): HBM-bound.
+// One thread = one point x 8 output channels: the point's xyz is a broadcast load, the
+// 8 x K weights and 8 biases sit in registers, and the 8 threads of a point write one
+// contiguous, fully coalesced output row.
+// =====================================================================================
+template <int K>
+__global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_args a) {
+  const int groups = a.n >> 3;                       // threads per point
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int cg = static_cast<int>(tid % groups) * 8;
+  float w[8][K], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    b[i] = a.bias ? a.bias[cg + i] : 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      w[i][k] = ld_as_float(a.w, static_cast<int64_t>(cg + i) * a.ldw + k, a.w_dtype);
+  }
+  const float* x = reinterpret_cast<const float*>(a.seg[0].ptr);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x / groups;
+  for (int64_t r = tid / groups; r < a.rows; r += stride) {
+    float xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = __ldg(x + r * a.seg[0].ld + k);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float acc = b[i];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc = fmaf(xv[k], w[i][k], acc);
+      v[i] = apply_act(acc, a.act, a.slope);
+    }
+    if (a.out_dtype == PCADV_F32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + r * a.ld_out + cg);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (a.out_dtype == PCADV_F16) {
+          __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f),
+                                        fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + r * a.ld_out + cg) =
+          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
 }  // namespace
 
+static bool first_layer_eligible(const pcadv_linear_args& a) {
+  const int esz = a.out_dtype == PCADV_F32 ? 4 : 2;
+  return a.num_seg == 1 && a.seg[0].k >= 1 && a.seg[0].k <= 4 && a.seg[0].dtype == PCADV_F32 &&
+         a.n % 8 == 0 && a.n <= 256 && 256 % (a.n / 8) == 0 && a.out && !a.group_bias && !a.addend && !a.mask &&
+         !a.out_scale && !a.colmax_key && !a.rowmax_key && (a.ld_out * esz) % 16 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.rows >= 1024;
+}
+
 int simt_linear(const pcadv_linear_args& a, cudaStream_t s) {
+  if (first_layer_eligible(a)) {
+    const int64_t threads = a.rows * (a.n / 8);
+    int64_t blocks = (threads + 255) / 256;
+    const int64_t cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    // n/8 divides the block size, so every thread keeps its channel group across the stride loop
+    switch (a.seg[0].k) {
+      case 1: first_layer_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a); break;
+      case 2: first_layer_kernel<2><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a); break;
+      case 3: first_layer_kernel<3><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a); break;
+      default: first_layer_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a); break;
+    }
+    PCADV_LAUNCHED();
+    return 0;
+  }
   const int64_t tiles_m = (a.rows + BM - 1) / BM;
   PCADV_CHECK_ARG(tiles_m <= 0x7fffffffLL, "pcadv_linear: too many rows");
   dim3 grid(static_cast<unsigned>(tiles_m), (a.n + BN - 1) / BN);

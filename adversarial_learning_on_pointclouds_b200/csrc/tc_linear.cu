@@ -55,7 +55,7 @@ __device__ __forceinline__ void tile_coords(const LinearParams& p, int64_t t, in
 
 template <bool kSwapped>
 __device__ __forceinline__ void producer_loop(const TensorMaps& maps, const LinearParams& p,
-                                              const SmemLayout& L) {
+                                              const SmemLayout& L, int nstages) {
   SharedTail* st = L.tail;
   const int64_t num_tiles = p.tiles_m * p.tiles_n;
   const uint32_t stage_tx = static_cast<uint32_t>((kTileM + p.bn) * kBlockK * 2);
@@ -80,14 +80,14 @@ __device__ __forceinline__ void producer_loop(const TensorMaps& maps, const Line
           tma_load_2d(sa, &maps.act[s], &st->full[stage], kk, m0);
           tma_load_2d(sb, &maps.w, &st->full[stage], kg, n0);
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   }
 }
 
 __device__ __forceinline__ void mma_loop(const LinearParams& p, const SmemLayout& L,
-                                         uint32_t tmem_base) {
+                                         uint32_t tmem_base, int nstages) {
   SharedTail* st = L.tail;
   const int64_t num_tiles = p.tiles_m * p.tiles_n;
   int total_chunks = 0;
@@ -106,7 +106,7 @@ __device__ __forceinline__ void mma_loop(const LinearParams& p, const SmemLayout
       const uint32_t a_addr = smem_u32(L.stages + stage * kStageBytes);
       mma_chunk_kmajor(d_tmem, a_addr, a_addr + kABytes, p.idesc, c == 0);
       umma_commit(&st->empty[stage]);          // frees the smem slot when the MMAs retire
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (++stage == nstages) { stage = 0; phase ^= 1; }
     }
     umma_commit(&st->tmem_full[buf]);          // accumulator complete -> epilogue
     if (++buf == 2) { buf = 0; buf_phase ^= 1; }
@@ -146,9 +146,9 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
   const int64_t num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
-    if (lane == 0) producer_loop<false>(maps, p, L);
+    if (lane == 0) producer_loop<false>(maps, p, L, kStages);
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(p, L, tmem_base);
+    if (lane == 0) mma_loop(p, L, tmem_base, kStages);
   } else {
     // ================= epilogue: 8 warps, two per TMEM lane quarter =================
     const int quarter = warp & 3;
@@ -394,9 +394,9 @@ tc_colmax_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) 
   const int64_t num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
-    if (lane == 0) producer_loop<true>(maps, p, L);
+    if (lane == 0) producer_loop<true>(maps, p, L, kMaxStages);
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(p, L, tmem_base);
+    if (lane == 0) mma_loop(p, L, tmem_base, kMaxStages);
   } else {
     // thread = output channel; TMEM columns = points.  Running (max, first index) per cloud.
     const int quarter = warp & 3;

@@ -6,7 +6,8 @@
 namespace pcadv {
 namespace tc {
 
-constexpr int kStages = 3;
+constexpr int kStages = 3;                        // ring depth of kernels that also stage an epilogue
+constexpr int kMaxStages = 4;                     // ring depth of kernels without epilogue staging
 constexpr int kBlockK = 64;                       // elements per K chunk = one 128-byte swizzle row
 constexpr int kTileM = 128;
 constexpr int kMaxTileN = 256;
@@ -28,8 +29,8 @@ struct TensorMaps {
 };
 
 struct SharedTail {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t mask_full[2];
@@ -54,10 +55,14 @@ __device__ __forceinline__ SmemLayout carve_smem(uint8_t* raw) {
 
 // one thread: barrier init; warp 1: TMEM allocation; everyone: publish
 __device__ __forceinline__ uint32_t pipeline_setup(const SmemLayout& L, int warp, int lane,
-                                                   uint32_t tmem_empty_count) {
+                                                   uint32_t tmem_empty_count,
+                                                   uint32_t empty_count = 1) {
   SharedTail* st = L.tail;
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&st->full[i], 1); mbar_init(&st->empty[i], 1); }
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&st->full[i], 1);
+      mbar_init(&st->empty[i], empty_count);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&st->tmem_full[i], 1);
       mbar_init(&st->tmem_empty[i], tmem_empty_count);

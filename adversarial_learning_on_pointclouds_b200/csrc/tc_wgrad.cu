@@ -23,8 +23,10 @@ struct WgradParams {
   int splits;
   int64_t rows_per_split; // multiple of 64
   uint32_t idesc;
+  int bf16;
   float* dw;
   int64_t ld_dw;
+  float* dbias;           // [n] or NULL: column sums of dz, formed from the smem tiles in flight
   const float* scale;
 };
 
@@ -40,7 +42,9 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
     tma_prefetch_desc(&maps.act[p.seg_index]);
     tma_prefetch_desc(&maps.w);
   }
-  const uint32_t tmem_base = pipeline_setup(L, warp, lane, 4);
+  // with a bias gradient the four epilogue warps also read every dz tile, so a stage is
+  // released by 1 (MMA commit) + 4 (epilogue warps) arrivals
+  const uint32_t tmem_base = pipeline_setup(L, warp, lane, 4, p.dbias ? 5 : 1);
   const int n_boxes = p.bn / 64;
   const uint32_t stage_tx = static_cast<uint32_t>((kTileM + p.bn) * kBlockK * 2);
 
@@ -71,7 +75,7 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
           for (int b = 0; b < n_boxes; ++b)
             tma_load_2d(sb + b * 8192, &maps.act[p.seg_index], &st->full[stage],
                         tn * p.bn + b * 64, static_cast<int32_t>(r));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kMaxStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -95,7 +99,7 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
           mma_chunk_mnmajor(d_tmem, a_addr, a_addr + kABytes, p.idesc, first);
           first = false;
           umma_commit(&st->empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kMaxStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&st->tmem_full[buf]);
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
@@ -107,9 +111,43 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
     int buf = 0;
     uint32_t buf_phase = 0;
     const float sc = p.scale ? *p.scale : 1.f;
+    int stage_e = 0;
+    uint32_t phase_e = 0;
     for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
       int tm, tn; int64_t r0, r1;
       decode(w, tm, tn, r0, r1);
+      float bsum = 0.f;
+      if (p.dbias) {
+        // bias gradient: thread = dz channel; sum its 64 rows of every stage straight from
+        // the swizzled smem tile ([64 rows][64 ch] boxes, 16-byte chunk index ^ (row & 7))
+        const uint32_t box_off = (lane_row >> 6) * 8192u;
+        const uint32_t cc = lane_row & 63;
+        for (int64_t r = r0; r < r1; r += kBlockK) {
+          mbar_wait(&st->full[stage_e], phase_e);
+          if (tn == 0) {
+            const uint8_t* tile = L.stages + stage_e * kStageBytes + box_off;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < kBlockK; rr += 2) {
+              const uint16_t a = *reinterpret_cast<const uint16_t*>(
+                  tile + rr * 128 + ((((cc >> 3) ^ (rr & 7)) << 4) | ((cc & 7) << 1)));
+              const uint16_t b = *reinterpret_cast<const uint16_t*>(
+                  tile + (rr + 1) * 128 + ((((cc >> 3) ^ ((rr + 1) & 7)) << 4) | ((cc & 7) << 1)));
+              if (p.bf16) {
+                s0 += __bfloat162float(__ushort_as_bfloat16(a));
+                s1 += __bfloat162float(__ushort_as_bfloat16(b));
+              } else {
+                s0 += __half2float(__ushort_as_half(a));
+                s1 += __half2float(__ushort_as_half(b));
+              }
+            }
+            bsum += s0 + s1;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st->empty[stage_e]);
+          if (++stage_e == kMaxStages) { stage_e = 0; phase_e ^= 1; }
+        }
+      }
       mbar_wait(&st->tmem_full[buf], buf_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -125,6 +163,7 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
         for (int j = 0; j < 32; ++j)
           if (k0 + j < p.seg_k) atomicAdd(dst + j, v[j] * sc);
       }
+      if (p.dbias && tn == 0 && c < p.n && r0 < r1) atomicAdd(p.dbias + c, bsum * sc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&st->tmem_empty[buf]);
@@ -163,7 +202,8 @@ int tc_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
     p.tiles_m = (a.n + kTileM - 1) / kTileM;
     p.tiles_n = (sg.k + p.bn - 1) / p.bn;
     const int tiles = p.tiles_m * p.tiles_n;
-    int64_t splits = (num_sms() + tiles - 1) / tiles;
+    // one wave: tiles * splits <= #SMs, so no CTA gets a second work item (a 2x tail)
+    int64_t splits = num_sms() / tiles;
     const int64_t max_splits = (a.rows + 511) / 512;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -173,14 +213,13 @@ int tc_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
     p.rows_per_split = rps;
     p.idesc = make_idesc(kTileM, p.bn, dt == PCADV_BF16, true, true);
     p.dw = a.dw; p.ld_dw = a.ld_dw; p.scale = a.scale;
+    p.bf16 = dt == PCADV_BF16 ? 1 : 0;
+    p.dbias = i == 0 ? a.dbias : nullptr;
     const int64_t work = static_cast<int64_t>(tiles) * p.splits;
     const int grid = static_cast<int>(work < num_sms() ? work : num_sms());
     tc_wgrad_kernel<<<grid, kWgradThreads, kSmemBytes, s>>>(maps, p);
     PCADV_LAUNCHED();
     koff += sg.k;
-  }
-  if (a.dbias) {
-    if (int rc = launch_colsum(a.dz, a.dz_dtype, a.ld_dz, a.rows, a.n, a.scale, a.dbias, s)) return rc;
   }
   if (a.dgroup_bias) {
     if (int rc = launch_group_colsum(a.dz, a.dz_dtype, a.ld_dz, a.rows, a.n, a.rows_per_group,

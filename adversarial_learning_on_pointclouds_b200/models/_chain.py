@@ -27,6 +27,9 @@ class Layer:
 def compute_weight(prec, w32, k_list, n):
     """The copy of a weight matrix the engine multiplies with: a 16-bit copy when
     the tensor-core engine can take the shape, else the fp32 master."""
+    ktot = sum(k_list)
+    if ktot != w32.shape[1]:                     # input carries zero-padded columns (K = 50 -> 64)
+        w32 = pad_cols(w32, ktot)
     if prec.engine == ENGINE_TC and all(k % 64 == 0 for k in k_list):
         return w32.to(prec.act_dtype)
     return w32
@@ -103,8 +106,8 @@ def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0)
     inv = scale2[1:2] if scale2 is not None else None
     ops.wgrad(dz, x_segs if need_w else [], dw=dw[:, :ktot] if need_w else None, dbias=db, scale=inv,
               engine=prec.engine)
-    n = w_shape[0]
-    return (dw[:n] if need_w else None), (db[:n] if need_b else None)
+    n, k = w_shape[0], w_shape[1]
+    return (dw[:n, :k] if need_w else None), (db[:n] if need_b else None)
 
 
 def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, scale2, addends=None):
@@ -130,7 +133,15 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
     dx = None
     if need_x:
         L = layers[0]
-        wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz.shape[1]])
+        k_in = L.w.shape[1]
+        wt = dgrad_weight(prec, [L.w], k_in, [dz.shape[1]])
+        if prec.scaled and k_in % 4:
+            # pad the output width so its rows are 16-byte aligned (TMA store); slice afterwards
+            k_pad = (k_in + 63) // 64 * 64
+            wt_p = wt.new_zeros((k_pad, wt.shape[1]))
+            wt_p[:k_in] = wt
+            wt = wt_p
         inv = scale2[1:2] if scale2 is not None else None
         dx, _, _ = ops.linear([dz], wt, out_dtype=torch.float32, out_scale=inv, engine=prec.engine)
+        dx = dx[:, :k_in]
     return grads, dx, dz

@@ -48,8 +48,9 @@ class PointMLPFunction(torch.autograd.Function):
         nl = len(spec.acts)
         layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
         x_in = x
-        if prec.scaled and x.shape[1] % 64 == 0 and x.shape[0] >= 128:
-            x_in = ops.convert(x, prec.act_dtype)            # 16-bit copy feeds the tensor cores
+        if prec.scaled and x.shape[1] >= 16 and x.shape[0] >= 128:
+            # 16-bit copy, K zero-padded to a multiple of 64, feeds the tensor cores
+            x_in = ops.convert(x, prec.act_dtype, cols_pad=(x.shape[1] + 63) // 64 * 64)
         body = layers if spec.reduce is None else layers[:-1]
         if gb is not None:
             gb = gb.contiguous().float()

@@ -117,17 +117,24 @@ class SegFunction(torch.autograd.Function):
             dg = dg + (dg_ext.float() * scale2[0] if prec.scaled else dg_ext.float())
         dw6 = torch.zeros((2048, 512), dtype=torch.float32, device=dev) if need["conv6.weight"] else None
         db6 = torch.zeros((2048,), dtype=torch.float32, device=dev) if need["conv6.bias"] else None
-        dx5_sparse = torch.zeros((P, 512), dtype=torch.float32, device=dev)
-        ops.maxpool_bwd(dg, g, idx, xs[4], W["conv6"], N, act=ACT_RELU, dw=dw6, dbias=db6,
-                        dx_acc=dx5_sparse, scale=inv)
-        grads["conv6.weight"], grads["conv6.bias"] = dw6, db6
-
         # ---- trunk: dz_k = relu'(x_k) * ([dz_{k+1} | dz_fc1] @ [W_{k+1}; fc1.W[:, slice_k]]) --
         s5 = _SLICES[4]
         wt = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512, [256])
-        dz, _, _ = ops.linear([dz_fc1], wt, addend=dx5_sparse, mask=xs[4], mask_act=ACT_RELU,
-                              out_dtype=prec.act_dtype, engine=prec.engine)
-        del dx5_sparse
+        w6 = compute_weight(prec, W["conv6"], [512], 2048)
+        if ops.maxpool_inplace_eligible(512, N, 2048):
+            # dense part first; the max-pool's sparse part (argmax rows only) is added in place
+            dz, _, _ = ops.linear([dz_fc1], wt, mask=xs[4], mask_act=ACT_RELU,
+                                  out_dtype=prec.act_dtype, engine=prec.engine)
+            ops.maxpool_bwd(dg, g, idx, xs[4], w6, N, act=ACT_RELU, dw=dw6, dbias=db6,
+                            dz_inout=dz, prev_act=ACT_RELU, scale=inv)
+        else:
+            dx5_sparse = torch.zeros((P, 512), dtype=torch.float32, device=dev)
+            ops.maxpool_bwd(dg, g, idx, xs[4], w6, N, act=ACT_RELU, dw=dw6, dbias=db6,
+                            dx_acc=dx5_sparse, scale=inv)
+            dz, _, _ = ops.linear([dz_fc1], wt, addend=dx5_sparse, mask=xs[4], mask_act=ACT_RELU,
+                                  out_dtype=prec.act_dtype, engine=prec.engine)
+            del dx5_sparse
+        grads["conv6.weight"], grads["conv6.bias"] = dw6, db6
         for li in range(4, 0, -1):                                    # conv5 .. conv2
             name = _TRUNK[li]
             xin = xs[li - 1]

@@ -239,9 +239,16 @@ def max_finalize(key, act=ACT_NONE, slope=0.0, want_idx=True):
     return val, idx
 
 
+def maxpool_inplace_eligible(k, rows_per_group, n):
+    """Shapes ``maxpool_bwd(dz_inout=...)`` takes (see include/pcadv.h)."""
+    return k % 64 == 0 and k <= 1024 and rows_per_group <= 8192 and n <= 4096
+
+
 def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0, dw=None,
-                dbias=None, dx_acc=None, scale=None):
-    """See ``pcadv_maxpool_bwd``."""
+                dbias=None, dx_acc=None, dz_inout=None, prev_act=ACT_NONE, prev_slope=0.0,
+                scale=None):
+    """See ``pcadv_maxpool_bwd``.  ``dz_inout`` ([rows, k], any float dtype) receives the
+    sparse contribution in place, through the previous layer's activation mask."""
     a = _lib.MaxBwdArgs()
     groups, n = dg.shape
     a.groups, a.n, a.k = groups, n, w.shape[1]
@@ -262,6 +269,9 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
         if dt != F32:
             raise ValueError("dx_acc must be fp32")
         a.dx_acc, a.ld_dx = p, ld
+    if dz_inout is not None:
+        a.dz_inout, a.ld_dz, a.dz_dtype = _mat(dz_inout)
+        a.prev_act, a.prev_slope = prev_act, float(prev_slope)
     a.scale = _f32(scale) if scale is not None else None
     _call("maxpool_bwd:n%d:k%d" % (n, a.k), _lib.lib().pcadv_maxpool_bwd, C.byref(a), _stream())
 

@@ -140,6 +140,9 @@ int pcadv_max_finalize(const unsigned long long* key, int64_t count, int32_t act
  *   dw[c, :]    += scale * dzc * x[r, :]
  *   dbias[c]    += scale * dzc
  *   dx_acc[r,:] += dzc * w[c, :]                (fp32 scatter-add, NOT scaled)
+ * or, instead of dx_acc, folded straight into the dz of the previous layer:
+ *   dz_inout[r,:] += prev_act'(x[r, :]) * sum_{c: row(g,c) = r} dzc * w[c, :]
+ *   (each touched row is summed in fp32 and added once; only argmax rows are touched)
  * Replaces the dense B x C x N scatter + dgrad + wgrad autograd runs.
  */
 typedef struct pcadv_maxbwd_args {
@@ -150,7 +153,11 @@ typedef struct pcadv_maxbwd_args {
   float slope;
   int32_t x_dtype;
   int32_t w_dtype;
-  int32_t reserved;
+  int32_t prev_act;           /* activation that produced x (for dz_inout) */
+  float prev_slope;
+  int32_t dz_dtype;
+  void* dz_inout;             /* [rows, k] or NULL */
+  int64_t ld_dz;
   int64_t rows_per_group;
   const float* dg;            /* [groups, n] */
   const float* gval;          /* [groups, n] pooled post-activation value */

@@ -103,6 +103,15 @@ def test_maxpool_bwd_matches_autograd():
     (gr * dg.double()).sum().backward()
     assert rel_err(g, gr) < 1e-5
     assert rel_err(dw, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5 and rel_err(dx, xr.grad) < 1e-5
+    # in-place form: dz += relu'(x) * dx, touching argmax rows only
+    for dt, tol in ((torch.float32, 1e-5), (torch.float16, 1e-3)):
+        dz0 = _rand((B * N, k), 9).to(dt)
+        dz = dz0.clone()
+        ops.maxpool_bwd(dg, g, idx, x.to(dt), w.to(dt), N, act=ACT_RELU, dz_inout=dz, prev_act=ACT_RELU)
+        ref = dz0.double() + (x.to(dt) > 0) * xr.grad
+        assert rel_err(dz, ref) < tol
+        touched = (xr.grad.abs().sum(1) > 0)
+        assert torch.equal(dz[~touched], dz0[~touched])
 
 
 def test_amax_scale_and_convert():
