@@ -72,6 +72,8 @@ SYMBOLS = {
     "pcadv_convert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                 C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "pcadv_convert_cm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "pcadv_transpose": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pcadv_version": (C.c_int, []),

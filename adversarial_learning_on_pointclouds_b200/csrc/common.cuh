@@ -62,6 +62,41 @@ __device__ __forceinline__ void st_from_float(void* p, int64_t i, int dtype, flo
   }
 }
 
+// 8 consecutive elements starting at element offset `off`: one / two 16-byte stores when the
+// address allows it, scalar stores otherwise
+__device__ __forceinline__ void store8(void* p, int64_t off, int dtype, const float (&o)[8]) {
+  if (dtype == PCADV_F32) {
+    float* q = reinterpret_cast<float*>(p) + off;
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      reinterpret_cast<float4*>(q)[0] = make_float4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<float4*>(q)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = o[j];
+    }
+    return;
+  }
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (dtype == PCADV_F16) {
+      __half2 h = __floats2half2_rn(fminf(fmaxf(o[2 * j], -65504.f), 65504.f),
+                                    fminf(fmaxf(o[2 * j + 1], -65504.f), 65504.f));
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  uint16_t* q = reinterpret_cast<uint16_t*>(p) + off;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+    *reinterpret_cast<uint4*>(q) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = static_cast<uint16_t>((pk[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+  }
+}
+
 __host__ __device__ __forceinline__ int dtype_size(int dtype) {
   return dtype == PCADV_F32 ? 4 : 2;
 }

@@ -182,7 +182,9 @@ __global__ void __launch_bounds__(256) maxbwd_rows_kernel(const pcadv_maxbwd_arg
     if (dzv[c] != 0.f) list[atomicAdd(&ends[a.idx[static_cast<int64_t>(g) * a.n + c]], 1)] = c;
   __syncthreads();
   const int pairs = a.k >> 6;
-  for (int r = warp; r < N; r += 8) {
+  // gridDim.y CTAs share a cloud (each rebuilds the cheap bucket table) and interleave its rows,
+  // so enough warps are in flight to hide the dependent gathers
+  for (int r = warp + 8 * blockIdx.y; r < N; r += 8 * gridDim.y) {
     const int beg = r == 0 ? 0 : ends[r - 1], end = ends[r];
     if (beg == end) continue;
     float2 acc[kMaxPairs];
@@ -219,13 +221,19 @@ __global__ void rowmax_bwd_kernel(const float* __restrict__ dy, const float* __r
                                   const int32_t* __restrict__ idx, int64_t rows, int n, int act,
                                   float slope, const float* scale, void* dz, int64_t ld_dz,
                                   int dz_dtype) {
+  // one thread = 8 consecutive columns of one row (n % 8 == 0 is checked by the caller)
+  const int per_row = n >> 3;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= rows * n) return;
-  const int64_t r = i / n;
-  const int c = static_cast<int>(i - r * n);
+  if (i >= rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c0 = static_cast<int>(i - r * per_row) << 3;
+  const int hit = idx[r] - c0;                     // 0..7 when the row's argmax is in this group
   float v = 0.f;
-  if (c == idx[r]) v = dy[r] * (scale ? *scale : 1.f) * act_grad_from_output(val[r], act, slope);
-  st_from_float(dz, r * ld_dz + c, dz_dtype, v);
+  if (hit >= 0 && hit < 8) v = dy[r] * (scale ? *scale : 1.f) * act_grad_from_output(val[r], act, slope);
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (j == hit) ? v : 0.f;
+  store8(dz, r * ld_dz + c0, dz_dtype, o);
 }
 
 __global__ void amax_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld,
@@ -259,7 +267,29 @@ __global__ void convert_kernel(const void* src, int src_dtype, int64_t ld_src, i
                                void* dst, int dst_dtype, int64_t ld_dst, int cols_pad,
                                const float* scale, const void* mask, int64_t ld_mask, int mask_dtype,
                                int mask_act, float mask_slope) {
+  // one thread = 8 consecutive output columns of one row (cols_pad % 8 == 0: 16-byte stores);
+  // the generic tail handles any other width
   const float sc = scale ? *scale : 1.f;
+  if ((cols_pad & 7) == 0) {
+    const int per_row = cols_pad >> 3;
+    const int64_t total = rows * per_row;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = i / per_row;
+      const int c0 = static_cast<int>(i - r * per_row) << 3;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float v = c < cols ? ld_as_float(src, r * ld_src + c, src_dtype) * sc : 0.f;
+        if (mask && c < cols)
+          v *= act_grad_from_output(ld_as_float(mask, r * ld_mask + c, mask_dtype), mask_act, mask_slope);
+        o[j] = v;
+      }
+      store8(dst, r * ld_dst + c0, dst_dtype, o);
+    }
+    return;
+  }
   const int64_t total = rows * cols_pad;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -269,6 +299,35 @@ __global__ void convert_kernel(const void* src, int src_dtype, int64_t ld_src, i
     if (mask && c < cols)
       v *= act_grad_from_output(ld_as_float(mask, r * ld_mask + c, mask_dtype), mask_act, mask_slope);
     st_from_float(dst, r * ld_dst + c, dst_dtype, v);
+  }
+}
+
+// channel-major B x C x N fp32 (what torch's softmax / log_softmax / their backward produce)
+// -> point-major [B*N, cols_pad] with scale, conversion and zero padding; a 32 x 32 tile
+// transpose through shared memory keeps both sides coalesced.
+__global__ void __launch_bounds__(256) convert_cm_kernel(const float* __restrict__ src,
+                                                        int64_t batch_stride, int64_t chan_stride,
+                                                        int64_t rows_per_group, int cols, void* dst,
+                                                        int dst_dtype, int64_t ld_dst, int cols_pad,
+                                                        const float* scale) {
+  __shared__ float tile[32][33];
+  const float sc = scale ? *scale : 1.f;
+  const int64_t b = blockIdx.z;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 32;     // point within the cloud
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc;
+    const int64_t i = i0 + tx;
+    tile[cc][tx] = (c < cols && i < rows_per_group)
+                       ? src[b * batch_stride + c * chan_stride + i] * sc : 0.f;
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int64_t i = i0 + rr;
+    const int c = c0 + tx;
+    if (i < rows_per_group && c < cols_pad)
+      st_from_float(dst, (b * rows_per_group + i) * ld_dst + c, dst_dtype, tile[tx][rr]);
   }
 }
 
@@ -340,7 +399,9 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
                                          (8192 + 2 * 4096) * 4));
       attr_done = true;
     }
-    maxbwd_rows_kernel<<<a->groups, 256, smem, s>>>(*a);
+    int split = 148 * 8 / a->groups;
+    split = split < 1 ? 1 : (split > 16 ? 16 : split);
+    maxbwd_rows_kernel<<<dim3(a->groups, split), 256, smem, s>>>(*a);
     PCADV_LAUNCHED();
   }
   if (a->dx_acc) {
@@ -355,9 +416,10 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
 extern "C" int pcadv_rowmax_bwd(const float* dy, const float* val, const int32_t* idx, int64_t rows,
                                 int32_t n, int32_t act, float slope, const float* scale, void* dz,
                                 int64_t ld_dz, int32_t dz_dtype, void* stream) {
-  PCADV_CHECK_ARG(dy && val && idx && dz && rows >= 0 && n > 0, "pcadv_rowmax_bwd: bad args");
+  PCADV_CHECK_ARG(dy && val && idx && dz && rows >= 0 && n > 0 && n % 8 == 0,
+                  "pcadv_rowmax_bwd: bad args (n must be a multiple of 8)");
   if (rows == 0) return 0;
-  const int64_t total = rows * n;
+  const int64_t total = rows * (n / 8);
   rowmax_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
                       static_cast<cudaStream_t>(stream)>>>(dy, val, idx, rows, n, act, slope, scale,
                                                            dz, ld_dz, dz_dtype);
@@ -386,9 +448,26 @@ extern "C" int pcadv_convert(const void* src, int32_t src_dtype, int64_t ld_src,
                              void* stream) {
   PCADV_CHECK_ARG(src && dst && rows >= 0 && cols > 0 && cols_pad >= cols, "pcadv_convert: bad args");
   if (rows == 0) return 0;
-  convert_kernel<<<grid_for(rows * cols_pad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int64_t work = (cols_pad & 7) == 0 ? rows * (cols_pad / 8) : rows * cols_pad;
+  convert_kernel<<<grid_for(work, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, src_dtype, ld_src, rows, cols, dst, dst_dtype, ld_dst, cols_pad, scale, mask, ld_mask,
       mask_dtype, mask_act, mask_slope);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int pcadv_convert_cm(const float* src, int64_t batch_stride, int64_t chan_stride,
+                                int64_t groups, int64_t rows_per_group, int32_t cols, void* dst,
+                                int32_t dst_dtype, int64_t ld_dst, int32_t cols_pad,
+                                const float* scale, void* stream) {
+  PCADV_CHECK_ARG(src && dst && groups >= 0 && rows_per_group > 0 && cols > 0 && cols_pad >= cols,
+                  "pcadv_convert_cm: bad args");
+  PCADV_CHECK_ARG(groups <= 65535, "pcadv_convert_cm: too many clouds (%lld)", (long long)groups);
+  if (groups == 0) return 0;
+  dim3 grid(static_cast<unsigned>((rows_per_group + 31) / 32), (cols_pad + 31) / 32,
+            static_cast<unsigned>(groups));
+  convert_cm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, batch_stride, chan_stride, rows_per_group, cols, dst, dst_dtype, ld_dst, cols_pad, scale);
   PCADV_LAUNCHED();
   return 0;
 }

@@ -41,16 +41,31 @@ class PointMLPFunction(torch.autograd.Function):
     def forward(ctx, prec, spec, x, gb, *params):
         if not x.is_cuda:
             raise RuntimeError("libpcadv layers need CUDA tensors; there is no CPU path")
-        if x.dim() != 2:
-            raise ValueError("PointMLPFunction expects [rows, k]")
-        if x.dtype != torch.float32 or x.stride(1) != 1:
-            x = x.contiguous().float()
         nl = len(spec.acts)
         layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
-        x_in = x
-        if prec.scaled and x.shape[1] >= 16 and x.shape[0] >= 128:
-            # 16-bit copy, K zero-padded to a multiple of 64, feeds the tensor cores
-            x_in = ops.convert(x, prec.act_dtype, cols_pad=(x.shape[1] + 63) // 64 * 64)
+        ctx.bcn = None
+        x_in = None
+        if x.dim() == 3:
+            # B x C x N map (what the trainers hand the discriminators).  Channel-major memory
+            # (torch softmax / log_softmax output) is transposed, converted and padded by one
+            # kernel; a transposed view of point-major storage (the generator's logits) is free.
+            B_, C_, N_ = x.shape
+            ctx.bcn = (B_, C_, N_)
+            to16 = prec.scaled and C_ >= 16 and B_ * N_ >= 128
+            if ops.is_channel_major(x):
+                x_in = ops.convert_cm(x, prec.act_dtype if to16 else torch.float32,
+                                      cols_pad=(C_ + 63) // 64 * 64 if to16 else C_)
+            else:
+                x = x.transpose(1, 2).reshape(B_ * N_, C_)
+        elif x.dim() != 2:
+            raise ValueError("PointMLPFunction expects [rows, k] or B x C x N")
+        if x_in is None:
+            if x.dtype != torch.float32 or x.stride(1) != 1:
+                x = x.contiguous().float()
+            x_in = x
+            if prec.scaled and x.shape[1] >= 16 and x.shape[0] >= 128:
+                # 16-bit copy, K zero-padded to a multiple of 64, feeds the tensor cores
+                x_in = ops.convert(x, prec.act_dtype, cols_pad=(x.shape[1] + 63) // 64 * 64)
         body = layers if spec.reduce is None else layers[:-1]
         if gb is not None:
             gb = gb.contiguous().float()
@@ -191,6 +206,9 @@ class PointMLPFunction(torch.autograd.Function):
             dw, db = grads[i] if grads[i] is not None else (None, None)
             flat.append(dw.reshape(params[2 * i].shape) if dw is not None else None)
             flat.append(db)
+        if dx is not None and ctx.bcn is not None:
+            B_, C_, N_ = ctx.bcn                                # back to B x C x N (a view)
+            dx = dx.reshape(B_, N_, dx.shape[1])[:, :, :C_].transpose(1, 2)
         return (None, None, dx, dgb, *flat)
 
 

@@ -79,14 +79,26 @@ class SegFunction(torch.autograd.Function):
 
         if dlogits is None:
             dlogits = torch.zeros((B, N, k_out), dtype=torch.float32, device=dev)
-        dl = dlogits.reshape(P, k_out)
-        if dl.stride(1) != 1 or dl.dtype != torch.float32:
-            dl = dl.contiguous().float()
-        scale2 = ops.amax_scale(dl) if prec.scaled else None
-        inv = scale2[1:2] if prec.scaled else None
+        dl_cm = dlogits.transpose(1, 2)                               # B x k x N
+        if dlogits.stride(2) != 1 and dl_cm.is_contiguous() and ops.is_channel_major(dl_cm):
+            # the trainer's CE / softmax backward hand the gradient over channel-major
+            # (B x k x N contiguous): one kernel transposes, scales, converts and pads it
+            scale2 = ops.amax_scale(dl_cm.reshape(B * k_out, N)) if prec.scaled else None
+            inv = scale2[1:2] if prec.scaled else None
+            if prec.scaled:
+                dz = ops.convert_cm(dl_cm, prec.act_dtype, cols_pad=(k_out + 63) // 64 * 64,
+                                    scale=scale2[0:1])
+            else:
+                dz = ops.convert_cm(dl_cm, torch.float32)
+        else:
+            dl = dlogits.reshape(P, k_out)
+            if dl.stride(1) != 1 or dl.dtype != torch.float32:
+                dl = dl.contiguous().float()
+            scale2 = ops.amax_scale(dl) if prec.scaled else None
+            inv = scale2[1:2] if prec.scaled else None
+            dz = prepare_dz(prec, dl, scale2)
 
         # ---- head: fc4, fc3, fc2 ---------------------------------------------------
-        dz = prepare_dz(prec, dl, scale2)
         head = (("fc4", ACT_NONE), ("fc3", ACT_RELU), ("fc2", ACT_RELU))
         for li, (name, _) in enumerate(head):
             xin = hs[2 - li]

@@ -24,10 +24,11 @@ def _prec(module):
 
 
 def _rows(x_bcn):
-    """B x C x N -> point-major [B*N, C] (a view when x is a transposed view of
-    point-major storage, as the generator's output is)."""
+    """The B x C x N map is handed to PointMLPFunction as is: it reads channel-major
+    memory (torch softmax output) and transposed views of point-major storage (the
+    generator's logits) without a torch-side copy."""
     B, C, N = x_bcn.shape
-    return x_bcn.transpose(1, 2).reshape(B * N, C), B, N
+    return x_bcn, B, N
 
 
 class ConvDiscNet(nn.Module):

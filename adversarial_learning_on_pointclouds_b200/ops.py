@@ -315,6 +315,24 @@ def convert(src, out_dtype, cols_pad=None, scale=None, mask=None, mask_act=ACT_N
     return dst
 
 
+def is_channel_major(x_bcn):
+    """True for a B x C x N fp32 tensor whose point axis has unit stride (contiguous
+    B x C x N, or any view with the same inner layout)."""
+    return x_bcn.dim() == 3 and x_bcn.dtype == torch.float32 and x_bcn.is_cuda and \
+        (x_bcn.shape[2] == 1 or x_bcn.stride(2) == 1) and x_bcn.stride(1) >= x_bcn.shape[2]
+
+
+def convert_cm(x_bcn, out_dtype, cols_pad=None, scale=None):
+    """Channel-major B x C x N fp32 -> point-major [B*N, cols_pad] (see pcadv_convert_cm)."""
+    B, Cn, N = x_bcn.shape
+    cols_pad = int(cols_pad or Cn)
+    dst = torch.empty((B * N, cols_pad), dtype=out_dtype, device=x_bcn.device)
+    _call("convert_cm:c%d" % cols_pad, _lib.lib().pcadv_convert_cm, _ptr(x_bcn), x_bcn.stride(0),
+          x_bcn.stride(1), B, N, Cn, _ptr(dst), _DT[out_dtype], cols_pad, cols_pad,
+          _f32(scale) if scale is not None else None, _stream())
+    return dst
+
+
 def transpose(src, out_dtype=None):
     """dst[c, r] = src[r, c] (weight matrices only)."""
     p, ld, dt = _mat(src)

@@ -195,6 +195,14 @@ int pcadv_convert(const void* src, int32_t src_dtype, int64_t ld_src, int64_t ro
                   const void* mask, int64_t ld_mask, int32_t mask_dtype, int32_t mask_act,
                   float mask_slope, void* stream);
 
+/* Same as pcadv_convert for a CHANNEL-MAJOR fp32 source: element (cloud b, channel c, point i)
+ * at src[b * batch_stride + c * chan_stride + i] -- the B x C x N layout torch's softmax /
+ * log_softmax (utils/trainer.py:901, :914) and their backward hand over -- written point-major
+ * to dst[(b * rows_per_group + i), c]. */
+int pcadv_convert_cm(const float* src, int64_t batch_stride, int64_t chan_stride, int64_t groups,
+                     int64_t rows_per_group, int32_t cols, void* dst, int32_t dst_dtype,
+                     int64_t ld_dst, int32_t cols_pad, const float* scale, void* stream);
+
 /* dst[c, r] = src[r, c] with conversion: builds the [k, n] copy of a weight
  * matrix that dgrad consumes. */
 int pcadv_transpose(const void* src, int32_t src_dtype, int64_t ld_src, int32_t rows, int32_t cols,

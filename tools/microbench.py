@@ -78,6 +78,20 @@ def cases(P, N):
     wg("wg_conv3", 128, [128])
     wg("wg_d2", 64, [64])
 
+    # sparse max-pool backward (conv6): realistic argmax distribution from a real forward
+    x5 = r16((P, 512)).relu_()
+    w6 = r16((2048, 512), 0.05)
+    _, key, _ = ops.linear([x5], w6, want_out=False, colmax=True, rows_per_group=N, engine=ENGINE_TC)
+    g6, idx6 = ops.max_finalize(key, ACT_RELU)
+    dg6 = torch.randn((B, 2048), device=DEV)
+    dw6 = torch.zeros((2048, 512), device=DEV)
+    db6 = torch.zeros((2048,), device=DEV)
+    dz5 = r16((P, 512))
+    c["maxbwd_dw"] = (lambda: ops.maxpool_bwd(dg6, g6, idx6, x5, w6, N, act=ACT_RELU, dw=dw6, dbias=db6),
+                      B * 2048 * 1024, 2.0 * B * 2048 * 512)
+    c["maxbwd_rows"] = (lambda: ops.maxpool_bwd(dg6, g6, idx6, x5, w6, N, act=ACT_RELU, dz_inout=dz5,
+                                                prev_act=ACT_RELU), B * 2048 * 1024, 2.0 * B * 2048 * 512)
+
     x50 = torch.randn((P, 50), device=DEV)
     w50 = torch.randn((64, 50), device=DEV) * 0.1
     c["disc1_simt"] = (lambda: ops.linear([x50], w50, bias=torch.zeros(64, device=DEV), act=ACT_RELU,
