@@ -49,7 +49,7 @@ class MaxBwdArgs(C.Structure):
         ("groups", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("act", C.c_int32),
         ("slope", C.c_float), ("x_dtype", C.c_int32), ("w_dtype", C.c_int32), ("prev_act", C.c_int32),
         ("prev_slope", C.c_float), ("dz_dtype", C.c_int32), ("dz_inout", C.c_void_p),
-        ("ld_dz", C.c_int64), ("rows_per_group", C.c_int64),
+        ("ld_dz", C.c_int64), ("workspace", C.c_void_p), ("rows_per_group", C.c_int64),
         ("dg", C.c_void_p), ("gval", C.c_void_p), ("idx", C.c_void_p),
         ("x", C.c_void_p), ("ldx", C.c_int64), ("w", C.c_void_p), ("ldw", C.c_int64),
         ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("dbias", C.c_void_p),

@@ -100,19 +100,37 @@ __global__ void __launch_bounds__(256) maxbwd_dw_fast_kernel(const pcadv_maxbwd_
 #pragma unroll
   for (int j = 0; j < kMaxPairs; ++j) acc[j] = make_float2(0.f, 0.f);
   float bsum = 0.f;
-  for (int g = warp; g < a.groups; g += 8) {
-    const int64_t gc = static_cast<int64_t>(g) * a.n + c;
-    const float dz = a.dg[gc] * act_grad_from_output(a.gval[gc], a.act, a.slope);
-    if (dz == 0.f) continue;
-    bsum += dz;
+  // four clouds per trip: the (dz, argmax row) lookups and then 4 x pairs row gathers are
+  // independent, so the dependent-load latency is paid once per four clouds
+  for (int g0 = warp; g0 < a.groups; g0 += 32) {
+    float dz[4];
+    int64_t r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + 8 * u;
+      dz[u] = 0.f;
+      r[u] = 0;
+      if (g < a.groups) {
+        const int64_t gc = static_cast<int64_t>(g) * a.n + c;
+        dz[u] = a.dg[gc] * act_grad_from_output(a.gval[gc], a.act, a.slope);
+        r[u] = static_cast<int64_t>(g) * a.rows_per_group + a.idx[gc];
+      }
+      bsum += dz[u];
+    }
     if (a.dw) {
-      const int64_t r = static_cast<int64_t>(g) * a.rows_per_group + a.idx[gc];
 #pragma unroll
       for (int j = 0; j < kMaxPairs; ++j) {
         if (j < pairs) {
-          const float2 x = ld_pair(a.x, r * a.ldx + 2 * lane + 64 * j, a.x_dtype);
-          acc[j].x = fmaf(dz, x.x, acc[j].x);
-          acc[j].y = fmaf(dz, x.y, acc[j].y);
+          float2 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            x[u] = dz[u] != 0.f ? ld_pair(a.x, r[u] * a.ldx + 2 * lane + 64 * j, a.x_dtype)
+                                : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[j].x = fmaf(dz[u], x[u].x, acc[j].x);
+            acc[j].y = fmaf(dz[u], x[u].y, acc[j].y);
+          }
         }
       }
     }
@@ -181,16 +199,57 @@ __global__ void __launch_bounds__(256) maxbwd_rows_kernel(const pcadv_maxbwd_arg
   for (int c = t; c < a.n; c += 256)
     if (dzv[c] != 0.f) list[atomicAdd(&ends[a.idx[static_cast<int64_t>(g) * a.n + c]], 1)] = c;
   __syncthreads();
+  // publish the bucket table: [ends (N) | list (n) | dz (n)] per cloud
+  int* ws = reinterpret_cast<int*>(a.workspace) + static_cast<int64_t>(g) * (N + 2 * a.n);
+  for (int r = t; r < N; r += 256) ws[r] = ends[r];
+  for (int c = t; c < a.n; c += 256) {
+    ws[N + c] = list[c];
+    reinterpret_cast<float*>(ws + N + a.n)[c] = dzv[c];
+  }
+}
+
+// one warp per row of the whole batch; rows no channel points at leave after two loads
+__global__ void __launch_bounds__(256) maxbwd_rows_apply_kernel(const pcadv_maxbwd_args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = static_cast<int>(a.rows_per_group);
+  const int64_t grow = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (grow >= static_cast<int64_t>(a.groups) * N) return;
+  const int g = static_cast<int>(grow / N), r = static_cast<int>(grow - static_cast<int64_t>(g) * N);
+  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 2 * a.n);
+  const int* ends = ws;
+  const int* list = ws + N;
+  const float* dzv = reinterpret_cast<const float*>(ws + N + a.n);
   const int pairs = a.k >> 6;
-  // gridDim.y CTAs share a cloud (each rebuilds the cheap bucket table) and interleave its rows,
-  // so enough warps are in flight to hide the dependent gathers
-  for (int r = warp + 8 * blockIdx.y; r < N; r += 8 * gridDim.y) {
+  {
     const int beg = r == 0 ? 0 : ends[r - 1], end = ends[r];
-    if (beg == end) continue;
+    if (beg == end) return;
     float2 acc[kMaxPairs];
 #pragma unroll
     for (int j = 0; j < kMaxPairs; ++j) acc[j] = make_float2(0.f, 0.f);
-    for (int q = beg; q < end; ++q) {
+    // a point that is the argmax of hundreds of channels makes this loop long: four
+    // channels per trip keep 4 x pairs independent gathers in flight
+    int q = beg;
+    for (; q + 4 <= end; q += 4) {
+      int c[4];
+      float dz[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { c[u] = list[q + u]; dz[u] = dzv[c[u]]; }
+#pragma unroll
+      for (int j = 0; j < kMaxPairs; ++j) {
+        if (j < pairs) {
+          float2 w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            w[u] = ld_pair(a.w, static_cast<int64_t>(c[u]) * a.ldw + 2 * lane + 64 * j, a.w_dtype);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[j].x = fmaf(dz[u], w[u].x, acc[j].x);
+            acc[j].y = fmaf(dz[u], w[u].y, acc[j].y);
+          }
+        }
+      }
+    }
+    for (; q < end; ++q) {
       const int c = list[q];
       const float dz = dzv[c];
 #pragma unroll
@@ -399,9 +458,11 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
                                          (8192 + 2 * 4096) * 4));
       attr_done = true;
     }
-    int split = 148 * 8 / a->groups;
-    split = split < 1 ? 1 : (split > 16 ? 16 : split);
-    maxbwd_rows_kernel<<<dim3(a->groups, split), 256, smem, s>>>(*a);
+    PCADV_CHECK_ARG(a->workspace != nullptr, "pcadv_maxpool_bwd: dz_inout needs a workspace");
+    maxbwd_rows_kernel<<<a->groups, 256, smem, s>>>(*a);
+    PCADV_LAUNCHED();
+    const int64_t total_rows = static_cast<int64_t>(a->groups) * a->rows_per_group;
+    maxbwd_rows_apply_kernel<<<static_cast<unsigned>((total_rows + 7) / 8), 256, 0, s>>>(*a);
     PCADV_LAUNCHED();
   }
   if (a->dx_acc) {

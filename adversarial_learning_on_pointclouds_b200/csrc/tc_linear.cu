@@ -163,6 +163,8 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
     int buf = 0;
     uint32_t buf_phase = 0;
     uint64_t slab_count = 0;
+    int staged_col = -1;                                 // what bias_s / gb_s currently hold
+    int64_t staged_g0 = -1, staged_g1 = -1;
     // mask prefetch iterator (issuer only): one 64-column slab ahead of the consumers
     int64_t pf_tile = blockIdx.x;
     int pf_step = 0;
@@ -191,9 +193,12 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
       const int64_t g = r_ok ? r / rpg : g_first;
       const bool gb_staged = p.group_bias != nullptr && (g_last - g_first) <= 1;
 
-      // ---- stage bias (and per-cloud bias rows) for this tile's columns
-      named_barrier_sync(1, 256);                        // previous tile's readers are done
-      {
+      // ---- stage bias (and per-cloud bias rows) for this tile's columns; skipped when the
+      // staged values are still the ones this tile needs (same columns, same clouds)
+      const bool restage = col_base != staged_col || (gb_staged && (g_first != staged_g0 || g_last != staged_g1));
+      if (restage) {
+        staged_col = col_base; staged_g0 = g_first; staged_g1 = g_last;
+        named_barrier_sync(1, 256);                      // previous tile's readers are done
         const int c = col_base + eid;
         const bool c_ok = eid < p.bn && c < p.n;
         bias_s[eid] = c_ok ? (p.bias ? __ldg(p.bias + c) : 0.f)
@@ -202,8 +207,8 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
           gb_s[eid] = c_ok ? __ldg(p.group_bias + g_first * p.n + c) : 0.f;
           gb_s[kMaxTileN + eid] = (c_ok && g_last != g_first) ? __ldg(p.group_bias + g_last * p.n + c) : 0.f;
         }
+        named_barrier_sync(1, 256);
       }
-      named_barrier_sync(1, 256);
 
       mbar_wait(&st->tmem_full[buf], buf_phase);
       tc_fence_after();
@@ -214,9 +219,16 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
         const int c0 = step * 64 + hsel * 32;
         const bool live = c0 < p.bn;
         const int sb = static_cast<int>(slab_count & 1);
+        // 16-bit outputs without a TMA-fetched mask rotate through all four slabs, so three
+        // stores can be in flight; otherwise two slabs (one pending store group)
+        const bool deep = (kOut != PCADV_F32) && !p.tma_mask;
+        const int ob = deep ? static_cast<int>(slab_count & 3) : sb;
         if (p.tma_out) {
-          // the slab(s) we are about to fill were handed to TMA stores two steps ago
-          if (is_issuer) bulk_wait_group_read<1>();
+          // the slab(s) we are about to fill were handed to TMA stores 2 (4) steps ago
+          if (is_issuer) {
+            if (deep) bulk_wait_group_read<3>();
+            else bulk_wait_group_read<1>();
+          }
           named_barrier_sync(1, 256);
           if (p.tma_mask) {
             if (is_issuer) issue_mask();
@@ -338,7 +350,7 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
                     pk[j] = *reinterpret_cast<uint32_t*>(&h);
                   }
                 }
-                uint8_t* orow = L.epi + sb * kSlabBytes + lane_row * 128;
+                uint8_t* orow = L.epi + ob * kSlabBytes + lane_row * 128;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                   *reinterpret_cast<uint4*>(orow + (((hsel * 4 + q) ^ (lane_row & 7)) << 4)) =
@@ -359,7 +371,7 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const LinearParams p) {
               if (step * 64 + 32 < p.bn)
                 tma_store_2d(&maps.out, L.epi + (2 * sb + 1) * kSlabBytes, col_base + step * 64 + 32, row0);
             } else {
-              tma_store_2d(&maps.out, L.epi + sb * kSlabBytes, col_base + step * 64, row0);
+              tma_store_2d(&maps.out, L.epi + ob * kSlabBytes, col_base + step * 64, row0);
             }
             bulk_commit_group();
           }

@@ -272,6 +272,8 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
     if dz_inout is not None:
         a.dz_inout, a.ld_dz, a.dz_dtype = _mat(dz_inout)
         a.prev_act, a.prev_slope = prev_act, float(prev_slope)
+        ws = torch.empty((groups * (int(rows_per_group) + 2 * n),), dtype=torch.int32, device=dg.device)
+        a.workspace = _ptr(ws)
     a.scale = _f32(scale) if scale is not None else None
     _call("maxpool_bwd:n%d:k%d" % (n, a.k), _lib.lib().pcadv_maxpool_bwd, C.byref(a), _stream())
 

@@ -26,7 +26,7 @@ def _device_label(like, value, random):
 
 def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
                          batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
-                         device_labels=False):
+                         device_labels=False, label_fn=None):
     """One iteration of run_training_seg (utils/trainer.py:873-966).
 
     batch_gt = (pts B x N x 3, cls B x 1 x 16, seg B x N), batch_nogt = (pts, cls),
@@ -37,6 +37,8 @@ def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimize
     pool_nogt = history_pool_nogt or ImagePool(0)
 
     def label(d_out, value, random):
+        if label_fn is not None:
+            return label_fn(d_out, value, random)
         if device_labels:
             return _device_label(d_out, value, random)
         return make_D_label(input=d_out, value=value, device=args.device, random=random)
@@ -73,3 +75,94 @@ def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimize
     optimizer.step()
     optimizer_D.step()
     return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
+
+
+class GraphedAdversarialSegStep:
+    """``adversarial_seg_step`` captured once into a CUDA graph and replayed.
+
+    One iteration launches ~950 kernels (645 libpcadv + the trainer-side torch ops); at cfg3
+    sizes the host cannot issue them as fast as the GPU retires them.  The captured graph
+    replays the identical kernel sequence from static buffers, so a step costs one launch.
+    The smoothed GAN labels keep the reference's semantics (utils/utils.py:22-31: drawn on the
+    CPU from torch's default generator): they are drawn into pinned host buffers and copied to
+    static device buffers before every replay.  Optimizers must be built with
+    ``capturable=True``.
+    """
+
+    def __init__(self, model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, args, batch_gt,
+                 batch_nogt, warmup=3, device_labels=False):
+        self.static_gt = tuple(t.clone() for t in batch_gt)
+        self.static_nogt = tuple(t.clone() for t in batch_nogt)
+        self.device_labels = device_labels
+        B, N = batch_nogt[0].shape[0], batch_nogt[0].shape[1]
+        Bg = batch_gt[0].shape[0]
+        dev = batch_gt[0].device
+        self.label_real = torch.empty((Bg, N), dtype=torch.float32, device=dev)
+        self.label_fake = torch.empty((B, N), dtype=torch.float32, device=dev)
+        # two pinned host slots: the labels of iteration i+1 are drawn while the GPU runs i
+        self.host_real = [torch.empty((Bg, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.host_fake = [torch.empty((B, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._copied = [None, None]
+        self._slot = 0
+
+        def label_fn(d_out, value, random):
+            if not random:
+                return torch.full_like(d_out, float(value))
+            if device_labels:
+                return _device_label(d_out, value, True)
+            return self.label_real if value == 1 else self.label_fake
+
+        def run():
+            return adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D,
+                                        self.static_gt, self.static_nogt, args, label_fn=label_fn)
+
+        self._draw_labels(0)
+        self._upload_labels()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        before = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = torch.stack(run())
+        self.launches_per_step = _lib.launch_count() - before
+
+    def _draw_labels(self, slot):
+        """Same draws, same order as make_D_label(random=True) at utils/trainer.py:940-945 and
+        :955-960 (CPU generator), into pinned host slot ``slot``."""
+        if self.device_labels:
+            return
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()          # its previous upload has left the buffer
+        self.host_real[slot].uniform_(0.7, 1.05)
+        self.host_fake[slot].uniform_(0.0, 0.305)
+
+    def _upload_labels(self):
+        if self.device_labels:
+            return
+        slot = self._slot
+        self.label_real.copy_(self.host_real[slot], non_blocking=True)
+        self.label_fake.copy_(self.host_fake[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._copied[slot] = ev
+
+    def __call__(self, batch_gt=None, batch_nogt=None):
+        """Copy the batch into the static buffers (skipped when None: reuse), draw labels, replay.
+        Returns the static 3-element loss tensor (l_seg, l_adv, l_D)."""
+        if batch_gt is not None:
+            for dst, src in zip(self.static_gt, batch_gt):
+                dst.copy_(src, non_blocking=True)
+        if batch_nogt is not None:
+            for dst, src in zip(self.static_nogt, batch_nogt):
+                dst.copy_(src, non_blocking=True)
+        self._upload_labels()
+        self.graph.replay()
+        self._slot ^= 1
+        self._draw_labels(self._slot)                  # next iteration's labels, under the GPU's shadow
+        return self.losses

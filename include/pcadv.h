@@ -158,6 +158,7 @@ typedef struct pcadv_maxbwd_args {
   int32_t dz_dtype;
   void* dz_inout;             /* [rows, k] or NULL */
   int64_t ld_dz;
+  void* workspace;            /* with dz_inout: >= groups * (rows_per_group + 2 * n) * 4 bytes */
   int64_t rows_per_group;
   const float* dg;            /* [groups, n] */
   const float* gval;          /* [groups, n] pooled post-activation value */
