@@ -62,6 +62,19 @@ __device__ __forceinline__ void st_from_float(void* p, int64_t i, int dtype, flo
   }
 }
 
+// two floats -> one packed 16-bit pair (lo in the low half); fp16 saturates to +-65504 instead
+// of producing inf (one F2FP.SATFINITE instruction)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // 8 consecutive elements starting at element offset `off`: one / two 16-byte stores when the
 // address allows it, scalar stores otherwise
 __device__ __forceinline__ void store8(void* p, int64_t off, int dtype, const float (&o)[8]) {

@@ -33,7 +33,7 @@ struct SharedTail {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t mask_full[2];
+  uint64_t mask_full[4];
   uint32_t tmem_base;
 };
 
@@ -66,8 +66,8 @@ __device__ __forceinline__ uint32_t pipeline_setup(const SmemLayout& L, int warp
     for (int i = 0; i < 2; ++i) {
       mbar_init(&st->tmem_full[i], 1);
       mbar_init(&st->tmem_empty[i], tmem_empty_count);
-      mbar_init(&st->mask_full[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&st->mask_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&st->tmem_base, kTmemCols);
