@@ -190,9 +190,30 @@ class PointNetSeg_regulization(nn.Module):
         self.fc3 = torch.nn.Linear(256, 128)
         self.fc4 = torch.nn.Linear(128, self.output_dim)
 
-    def forward(self, x, cls):
-        raise NotImplementedError(
-            "PointNetSeg_regulization is not built yet (SURVEY.md 8a row a7, marked next)")
+    def forward(self, x, cls):                  # B x N x 3, B x 1 x 16
+        # Composition of the generic Functions (fp32 tensors between them); the fused
+        # single-Function path is PointNetSeg's -- this variant is not on the benchmarked path.
+        B, N, _ = x.shape
+        P = B * N
+        prec = _prec(self)
+        trans = self.stn._run(x)                                        # :229  B x 3 x 3
+        xt = BmmFunction.apply(x, trans).reshape(P, 3)                  # :230-232
+        x1 = point_mlp(prec, xt, [self.conv1], [_RELU])
+        x2 = point_mlp(prec, x1, [self.conv2], [_RELU])
+        x3 = point_mlp(prec, x2, [self.conv3], [_RELU])
+        trans_feat = self.fstn._run(x3.view(B, N, 128))                 # :237  B x 128 x 128
+        h = BmmFunction.apply(x3.view(B, N, 128), trans_feat).reshape(P, 128)   # :238-239
+        x4 = point_mlp(prec, h, [self.conv4], [_RELU])
+        x5 = point_mlp(prec, x4, [self.conv5], [_RELU])
+        g = point_mlp(prec, x5, [self.conv6], [_RELU], reduce="points", group=N)   # B x 2048
+        # concat fold (:246-251): global feature and class one-hot become a per-cloud bias
+        w1 = self.fc1.weight
+        cb = point_mlp(prec, torch.cat([g, cls.reshape(B, -1).float()], 1),
+                       [(w1[:, 960:], self.fc1.bias)], [_NONE])          # B x 256
+        logits = point_mlp(prec, torch.cat([x1, x2, x3, x4, x5], 1),
+                           [(w1[:, :960], None), self.fc2, self.fc3, self.fc4],
+                           [_RELU, _RELU, _RELU, _NONE], group=N, group_bias=cb)   # P x k
+        return logits.view(B, N, -1).transpose(1, 2), g.unsqueeze(2), trans_feat
 
 
 class PointNetDenseCls(nn.Module):

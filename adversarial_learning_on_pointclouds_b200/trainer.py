@@ -80,7 +80,7 @@ def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimize
 class GraphedAdversarialSegStep:
     """``adversarial_seg_step`` captured once into a CUDA graph and replayed.
 
-    One iteration launches ~950 kernels (645 libpcadv + the trainer-side torch ops); at cfg3
+    One iteration launches ~400 kernels (123 libpcadv + the trainer-side torch ops); at cfg3
     sizes the host cannot issue them as fast as the GPU retires them.  The captured graph
     replays the identical kernel sequence from static buffers, so a step costs one launch.
     The smoothed GAN labels keep the reference's semantics (utils/utils.py:22-31: drawn on the

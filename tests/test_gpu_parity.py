@@ -414,3 +414,81 @@ def test_launch_counter_counts():
     x = _rand((256, 64), 1)
     ops.linear([x], _rand((64, 64), 2))
     assert pkg._lib.launch_count() == before + 1
+
+
+# ------------------------------------------------------- PointNetSeg_regulization (a7)
+@pytest.mark.parametrize("mode", MODES)
+def test_seg_regulization_golden(golden, mode):
+    G = golden["small_seg_regu"]
+    net = build_seg(3, 11, regu=True).to(DEV)
+    for mod in net.modules():
+        mod.precision = Precision(mode)
+    check_weights(net, G["weights"])
+    pts, _, seg, cls = inputs(3, 200, 77)
+    pred, glob, tf = net(pts.to(DEV), cls.to(DEV))
+    reg = M.feature_transform_regularizer(tf)
+    loss = F.cross_entropy(pred, seg.to(DEV)) + 0.5 * glob.square().mean() + 1e-3 * reg
+    loss.backward()
+    tol = TOL[mode]
+    assert tuple(pred.shape) == (3, 50, 200) and tuple(tf.shape) == (3, 128, 128)
+    assert abs(loss.item() - G["loss"]) < 10 * tol * abs(G["loss"])
+    assert rel_err(pred, G["pred"]) < 4 * tol and rel_err(glob, G["glob"]) < 4 * tol
+    if mode == "fp32":
+        for k, v in net.named_parameters():
+            assert_summary_close(v.grad, G["grads"][k], 3e-4, k)
+
+
+# ------------------------------------ BASELINE full sizes: size-independent properties
+def test_full_size_properties_cfg5():
+    """cfg5 shape (B=256, N=4096 per pass, 2^20 points), fast mode.  The oracle cannot run
+    this size, so the checks are properties of the path: a cloud's output does not depend on
+    the rest of the batch (bit-exact), permuting a cloud's points permutes its logits and
+    leaves the pooled feature unchanged, and the backward is linear in the incoming gradient."""
+    B, N = 256, 4096
+    net = build_seg(0).to(DEV)
+    net.precision = Precision("fp16")
+    pts, _, seg, cls = inputs(B, N, 1234)
+    pts, cls, seg = pts.to(DEV), cls.to(DEV), seg.to(DEV)
+    with torch.no_grad():
+        pred, glob = net(pts, cls)
+        sub, gsub = net(pts[37:41], cls[37:41])
+        assert torch.equal(pred[37:41], sub) and torch.equal(glob[37:41], gsub)
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(5)).to(DEV)
+        p2, g2 = net(pts[:8][:, perm], cls[:8])
+        assert torch.equal(g2, glob[:8])
+        assert torch.equal(p2, pred[:8][:, :, perm])
+    assert torch.isfinite(pred).all()
+    # linearity of the backward in dL/dlogits: a power-of-two factor only shifts the dynamic
+    # gradient scale, so the two runs differ by the order of the fp32 RED accumulation in wgrad
+    small = (pts[:16], cls[:16])
+    grads = []
+    for factor in (1.0, 4.0):
+        net.zero_grad()
+        pr, _ = net(*small)
+        (F.cross_entropy(pr, seg[:16]) * factor).backward()
+        grads.append({k: v.grad.clone() for k, v in net.named_parameters()})
+    for k in grads[0]:
+        assert rel_err(grads[1][k], 4.0 * grads[0][k]) < 1e-4, k
+
+
+def test_full_size_adversarial_step_runs_cfg5_shapes():
+    """One adversarial iteration at the benchmark's per-GPU size (reduced to 64+64 clouds to
+    keep the test short): finite losses, every parameter of G and D updated."""
+    from adversarial_learning_on_pointclouds_b200.trainer import adversarial_seg_step
+    import argparse
+    B, N = 64, 4096
+    torch.manual_seed(0)
+    g = init_net(M.PointNetSeg(50), "cpu", "xavier").to(DEV)
+    d = init_net(M.PointwiseDiscNet(N, 50), "cpu", "xavier").to(DEV)
+    before = {k: v.clone() for k, v in list(g.state_dict().items()) + list(d.state_dict().items())}
+    opt = torch.optim.Adam(g.parameters(), lr=1e-4)
+    optD = torch.optim.Adam(d.parameters(), lr=1e-5)
+    pts, _, seg, cls = inputs(B, N, 1234)
+    pts2, _, _, cls2 = inputs(B, N, 4321)
+    args = argparse.Namespace(device=DEV, lambda_seg=1.0, lambda_adv=1e-3)
+    losses = adversarial_seg_step(g, d, torch.nn.BCEWithLogitsLoss(), torch.nn.CrossEntropyLoss(), opt,
+                                  optD, (pts.to(DEV), cls.to(DEV), seg.to(DEV)),
+                                  (pts2.to(DEV), cls2.to(DEV)), args)
+    assert all(torch.isfinite(l) for l in losses)
+    after = dict(list(g.state_dict().items()) + list(d.state_dict().items()))
+    assert all(not torch.equal(before[k], after[k]) for k in before)

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--device-labels", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="also list torch ops by input shape")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     Bg, Bn, N = bench.WORKLOADS[args.workload]
@@ -46,10 +47,20 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.shapes) as prof:
         for _ in range(args.steps):
             step()
         torch.cuda.synchronize()
+    if args.shapes:
+        ops_rows = []
+        for e in prof.key_averages(group_by_input_shape=True):
+            t = getattr(e, "device_time_total", 0) or 0
+            if e.key.startswith("aten::") and t > 0:
+                ops_rows.append((t / args.steps / 1e3, e.count / args.steps, e.key, str(e.input_shapes)[:90]))
+        ops_rows.sort(reverse=True)
+        print("torch ops by device time (ms/step):")
+        for ms, cnt, key, shp in ops_rows[:30]:
+            print("%8.3f ms  %5.1f  %-28s %s" % (ms, cnt, key, shp))
     rows = []
     for e in prof.key_averages():
         t = getattr(e, "device_time_total", None)
