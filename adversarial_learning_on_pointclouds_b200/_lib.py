@@ -67,6 +67,13 @@ SYMBOLS = {
     "pcadv_rowmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_int32, C.c_void_p]),
+    "pcadv_rowmax_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "pcadv_rowmax_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pcadv_amax_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcadv_convert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,

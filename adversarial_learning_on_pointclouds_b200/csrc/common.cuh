@@ -75,6 +75,36 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// 8 consecutive elements starting at element offset `off` as floats (vector loads when aligned)
+__device__ __forceinline__ void load8(const void* p, int64_t off, int dtype, float (&o)[8]) {
+  if (dtype == PCADV_F32) {
+    const float* q = reinterpret_cast<const float*>(p) + off;
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      const float4 a = reinterpret_cast<const float4*>(q)[0], b = reinterpret_cast<const float4*>(q)[1];
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = q[j];
+    }
+    return;
+  }
+  const uint16_t* q = reinterpret_cast<const uint16_t*>(p) + off;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+    const uint4 t4 = *reinterpret_cast<const uint4*>(q);
+    const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f;
+      if (dtype == PCADV_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+      else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+      o[2 * e] = f.x; o[2 * e + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = ld_as_float(p, off + j, dtype);
+  }
+}
+
 // 8 consecutive elements starting at element offset `off`: one / two 16-byte stores when the
 // address allows it, scalar stores otherwise
 __device__ __forceinline__ void store8(void* p, int64_t off, int dtype, const float (&o)[8]) {

@@ -295,6 +295,68 @@ __global__ void rowmax_bwd_kernel(const float* __restrict__ dy, const float* __r
   store8(dz, r * ld_dz + c0, dz_dtype, o);
 }
 
+// Backward of "layer + activation + max over channels" (models/discriminator.py:67-72) without
+// the dense one-hot dz: per row only channel idx[r] carries gradient s[r] = dy[r] * act'(val[r]).
+//   dgrad:  dz_prev[r, :] = prev_act'(y_prev[r, :]) * (scale * s[r]) * w[idx[r], :]
+__global__ void rowmax_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ val,
+                                    const int32_t* __restrict__ idx, int64_t rows, int k, int act,
+                                    float slope, const float* scale, const void* w, int64_t ldw,
+                                    int w_dtype, const void* yprev, int64_t ld_y, int y_dtype,
+                                    int prev_act, float prev_slope, void* dz, int64_t ld_dz,
+                                    int dz_dtype) {
+  const int per_row = k >> 3;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c0 = static_cast<int>(i - r * per_row) << 3;
+  const float s = dy[r] * (scale ? *scale : 1.f) * act_grad_from_output(val[r], act, slope);
+  float wv[8], yv[8], o[8];
+  load8(w, static_cast<int64_t>(idx[r]) * ldw + c0, w_dtype, wv);
+  load8(yprev, r * ld_y + c0, y_dtype, yv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = s * wv[j] * act_grad_from_output(yv[j], prev_act, prev_slope);
+  store8(dz, r * ld_dz + c0, dz_dtype, o);
+}
+
+//   wgrad:  dw[idx[r], :] += s[r] * y_prev[r, :],  dbias[idx[r]] += s[r]   (fp32, no scaling
+//   needed).  Per-CTA shared-memory accumulators [n x k] take the scatter; one global atomicAdd
+//   per (CTA, element) at the end.
+__global__ void __launch_bounds__(256) rowmax_wgrad_kernel(const float* __restrict__ dy,
+                                                          const float* __restrict__ val,
+                                                          const int32_t* __restrict__ idx,
+                                                          int64_t rows, int n, int k, int act,
+                                                          float slope, const void* yprev, int64_t ld_y,
+                                                          int y_dtype, float* dw, int64_t ld_dw,
+                                                          float* dbias) {
+  extern __shared__ float acc_s[];                       // [n * k] + [n]
+  float* bias_s = acc_s + static_cast<size_t>(n) * k;
+  for (int e = threadIdx.x; e < n * k + n; e += blockDim.x) acc_s[e] = 0.f;
+  __syncthreads();
+  const int per_row = k >> 3;
+  const int64_t total = rows * per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / per_row;
+    const int c0 = static_cast<int>(i - r * per_row) << 3;
+    const float s = dy[r] * act_grad_from_output(val[r], act, slope);
+    if (s == 0.f) continue;
+    const int ch = idx[r];
+    float yv[8];
+    load8(yprev, r * ld_y + c0, y_dtype, yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&acc_s[ch * k + c0 + j], s * yv[j]);
+    if (c0 == 0) atomicAdd(&bias_s[ch], s);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * k; e += blockDim.x) {
+    const float v = acc_s[e];
+    if (v != 0.f && dw) atomicAdd(&dw[static_cast<int64_t>(e / k) * ld_dw + (e % k)], v);
+  }
+  if (dbias)
+    for (int e = threadIdx.x; e < n; e += blockDim.x)
+      if (bias_s[e] != 0.f) atomicAdd(&dbias[e], bias_s[e]);
+}
+
 __global__ void amax_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld,
                             unsigned int* ws) {
   float m = 0.f;
@@ -484,6 +546,47 @@ extern "C" int pcadv_rowmax_bwd(const float* dy, const float* val, const int32_t
   rowmax_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
                       static_cast<cudaStream_t>(stream)>>>(dy, val, idx, rows, n, act, slope, scale,
                                                            dz, ld_dz, dz_dtype);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int pcadv_rowmax_dgrad(const float* dy, const float* val, const int32_t* idx, int64_t rows,
+                                  int32_t k, int32_t act, float slope, const float* scale,
+                                  const void* w, int64_t ldw, int32_t w_dtype, const void* yprev,
+                                  int64_t ld_y, int32_t y_dtype, int32_t prev_act, float prev_slope,
+                                  void* dz, int64_t ld_dz, int32_t dz_dtype, void* stream) {
+  PCADV_CHECK_ARG(dy && val && idx && w && yprev && dz && rows >= 0 && k > 0 && k % 8 == 0,
+                  "pcadv_rowmax_dgrad: bad args (k must be a multiple of 8)");
+  if (rows == 0) return 0;
+  const int64_t total = rows * (k / 8);
+  rowmax_dgrad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(dy, val, idx, rows, k, act, slope, scale, w,
+                                                             ldw, w_dtype, yprev, ld_y, y_dtype,
+                                                             prev_act, prev_slope, dz, ld_dz, dz_dtype);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int pcadv_rowmax_wgrad(const float* dy, const float* val, const int32_t* idx, int64_t rows,
+                                  int32_t n, int32_t k, int32_t act, float slope, const void* yprev,
+                                  int64_t ld_y, int32_t y_dtype, float* dw, int64_t ld_dw,
+                                  float* dbias, void* stream) {
+  PCADV_CHECK_ARG(dy && val && idx && yprev && rows >= 0 && n > 0 && k > 0 && k % 8 == 0,
+                  "pcadv_rowmax_wgrad: bad args (k must be a multiple of 8)");
+  const size_t smem = (static_cast<size_t>(n) * k + n) * sizeof(float);
+  PCADV_CHECK_ARG(smem <= 200 * 1024, "pcadv_rowmax_wgrad: n * k too large (%d x %d)", n, k);
+  if (rows == 0) return 0;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    PCADV_CUDA_OK(cudaFuncSetAttribute(rowmax_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+    attr = 200 * 1024;
+  }
+  const int64_t total = rows * (k / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  rowmax_wgrad_kernel<<<static_cast<unsigned>(blocks), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      dy, val, idx, rows, n, k, act, slope, yprev, ld_y, y_dtype, dw, ld_dw, dbias);
   PCADV_LAUNCHED();
   return 0;
 }

@@ -370,7 +370,88 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_arg
   }
 }
 
+// First-layer weight gradient (K <= 4): dw[c, k] = scale * sum_r dz[r, c] * x[r, k], HBM-bound.
+// Same mapping as first_layer_kernel: 8 threads per point, each owning 8 channels; per-thread
+// register accumulators over a grid-stride range of points, then shuffle + shared-memory
+// reduction and one atomicAdd per (CTA, element).
+template <int K>
+__global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const pcadv_wgrad_args a) {
+  __shared__ float red[8][32][8 * (K + 1)];          // [warp][channel group][8 x (K weights + bias)]
+  const int groups = a.n >> 3;                       // threads per point (divides 32)
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int grp = static_cast<int>(tid % groups);
+  const int cg = grp * 8;
+  const float* x = reinterpret_cast<const float*>(a.seg[0].ptr);
+  float acc[8][K + 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k <= K; ++k) acc[i][k] = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x / groups;
+  for (int64_t r = tid / groups; r < a.rows; r += stride) {
+    float xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = __ldg(x + r * a.seg[0].ld + k);
+    float dz[8];
+    if (a.dz_dtype == PCADV_F32) {
+      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dz) + r * a.ld_dz + cg);
+      const float4 u = p[0], v = p[1];
+      dz[0] = u.x; dz[1] = u.y; dz[2] = u.z; dz[3] = u.w; dz[4] = v.x; dz[5] = v.y; dz[6] = v.z; dz[7] = v.w;
+    } else {
+      const uint4 t4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.dz) + r * a.ld_dz + cg);
+      const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f;
+        if (a.dz_dtype == PCADV_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+        else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+        dz[2 * e] = f.x; dz[2 * e + 1] = f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[i][k] = fmaf(dz[i], xv[k], acc[i][k]);
+      acc[i][K] += dz[i];
+    }
+  }
+  // lanes that share a channel group are `groups` apart
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+      float v = acc[i][k];
+      for (int o = 16; o >= groups; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[i][k] = v;
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < groups) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k <= K; ++k) red[warp][lane][i * (K + 1) + k] = acc[i][k];
+  }
+  __syncthreads();
+  const float sc = a.scale ? *a.scale : 1.f;
+  for (int e = threadIdx.x; e < groups * 8 * (K + 1); e += 256) {
+    const int gq = e / (8 * (K + 1)), rem = e % (8 * (K + 1));
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][gq][rem];
+    const int c = gq * 8 + rem / (K + 1), k = rem % (K + 1);
+    if (k < K) { if (a.dw) atomicAdd(&a.dw[static_cast<int64_t>(c) * a.ld_dw + k], v * sc); }
+    else if (a.dbias) atomicAdd(&a.dbias[c], v * sc);
+  }
+}
+
 }  // namespace
+
+static bool first_layer_wgrad_eligible(const pcadv_wgrad_args& a) {
+  const int esz = a.dz_dtype == PCADV_F32 ? 4 : 2;
+  return a.num_seg == 1 && a.seg[0].k >= 1 && a.seg[0].k <= 4 && a.seg[0].dtype == PCADV_F32 &&
+         a.n % 8 == 0 && a.n <= 256 && 32 % (a.n / 8) == 0 && !a.dgroup_bias &&
+         (a.ld_dz * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.dz) & 15) == 0 && a.rows >= 1024;
+}
 
 static bool first_layer_eligible(const pcadv_linear_args& a) {
   const int esz = a.out_dtype == PCADV_F32 ? 4 : 2;
@@ -426,6 +507,17 @@ int launch_colsum(const void* dz, int dz_dtype, int64_t ld, int64_t rows, int n,
 }
 
 int simt_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
+  if ((a.dw || a.dbias) && first_layer_wgrad_eligible(a)) {
+    const unsigned blocks = 148 * 4;
+    switch (a.seg[0].k) {
+      case 1: first_layer_wgrad_kernel<1><<<blocks, 256, 0, s>>>(a); break;
+      case 2: first_layer_wgrad_kernel<2><<<blocks, 256, 0, s>>>(a); break;
+      case 3: first_layer_wgrad_kernel<3><<<blocks, 256, 0, s>>>(a); break;
+      default: first_layer_wgrad_kernel<4><<<blocks, 256, 0, s>>>(a); break;
+    }
+    PCADV_LAUNCHED();
+    return 0;
+  }
   if (a.dw) {
     int koff = 0;
     for (int i = 0; i < a.num_seg; ++i) {

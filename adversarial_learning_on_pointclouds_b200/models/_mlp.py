@@ -144,7 +144,23 @@ class PointMLPFunction(torch.autograd.Function):
         elif d_out is not None:
             L = layers[-1]
             src = ys[-1] if ys else x_in
-            if spec.reduce == "channels":
+            if spec.reduce == "channels" and body and src.shape[1] % 8 == 0 and \
+                    L.w.shape[0] * src.shape[1] <= 48000 and (len(body) - 1) not in addends:
+                # only channel idx[r] of a row carries gradient: gather / scatter kernels instead
+                # of a dense one-hot dz and two GEMMs over it
+                n, k_true = L.w.shape
+                dy = d_out.reshape(-1)
+                if need_w[-1] or need_b[-1]:
+                    dw = torch.zeros((n, src.shape[1]), dtype=torch.float32, device=dev) if need_w[-1] else None
+                    db = torch.zeros((n,), dtype=torch.float32, device=dev) if need_b[-1] else None
+                    ops.rowmax_wgrad(dy, red_val, red_idx, src, n, act=L.act, slope=L.slope, dw=dw, dbias=db)
+                    grads[-1] = (dw[:, :k_true] if dw is not None else None, db)
+                P_ = body[-1]
+                w_pad = compute_weight(prec, L.w, [src.shape[1]], n)
+                dz_last = ops.rowmax_dgrad(dy, red_val, red_idx, w_pad, src, act=L.act, slope=L.slope,
+                                           scale=S, prev_act=P_.act, prev_slope=P_.slope,
+                                           out_dtype=prec.act_dtype)
+            elif spec.reduce == "channels":
                 n = L.w.shape[0]
                 dz_red = ops.rowmax_bwd(d_out.reshape(-1), red_val, red_idx, n, act=L.act,
                                         slope=L.slope, scale=S, out_dtype=prec.act_dtype)

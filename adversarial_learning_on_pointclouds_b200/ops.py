@@ -287,6 +287,35 @@ def rowmax_bwd(dy, val, idx, n, *, act=ACT_NONE, slope=0.0, scale=None, out_dtyp
     return dz
 
 
+def rowmax_dgrad(dy, val, idx, w, yprev, *, act=ACT_NONE, slope=0.0, scale=None, prev_act=ACT_NONE,
+                 prev_slope=0.0, out_dtype=torch.float32):
+    """dz of the layer BEFORE a max over channels, straight from (dy, argmax): see
+    ``pcadv_rowmax_dgrad``.  w: the pooled layer's [n, k] weight, yprev: its [rows, k] input."""
+    rows, k = yprev.shape
+    wp, ldw, wdt = _mat(w)
+    yp, ldy, ydt = _mat(yprev)
+    dz = torch.empty((rows, k), dtype=out_dtype, device=yprev.device)
+    _call("rowmax_dgrad:k%d" % k, _lib.lib().pcadv_rowmax_dgrad, _f32(dy), _f32(val), _ptr(idx), rows, k,
+          act, float(slope), _f32(scale) if scale is not None else None, wp, ldw, wdt, yp, ldy, ydt,
+          prev_act, float(prev_slope), _ptr(dz), k, _DT[out_dtype], _stream())
+    return dz
+
+
+def rowmax_wgrad(dy, val, idx, yprev, n, *, act=ACT_NONE, slope=0.0, dw=None, dbias=None):
+    """fp32 (dw [n, k], dbias [n]) of a layer followed by a max over channels, accumulated
+    into: see ``pcadv_rowmax_wgrad``."""
+    rows, k = yprev.shape
+    yp, ldy, ydt = _mat(yprev)
+    dwp, ld_dw = (C.c_void_p(0), 0)
+    if dw is not None:
+        dwp, ld_dw, dt = _mat(dw)
+        if dt != F32:
+            raise ValueError("dw must be fp32")
+    _call("rowmax_wgrad:n%d:k%d" % (n, k), _lib.lib().pcadv_rowmax_wgrad, _f32(dy), _f32(val), _ptr(idx),
+          rows, n, k, act, float(slope), yp, ldy, ydt, dwp, ld_dw,
+          _f32(dbias) if dbias is not None else None, _stream())
+
+
 def amax_scale(xs, target=256.0):
     """Device-side power-of-two gradient scale over one or several fp32 matrices:
     returns a 2-float tensor [S, 1/S] with S = 2^floor(log2(target / max|x|))."""

@@ -183,6 +183,20 @@ int pcadv_rowmax_bwd(const float* dy, const float* val, const int32_t* idx, int6
                      int32_t act, float slope, const float* scale, void* dz, int64_t ld_dz,
                      int32_t dz_dtype, void* stream);
 
+/* The same backward without materialising the one-hot dz (models/discriminator.py:67-72),
+ * with s[r] = dy[r] * act'(val[r]):
+ *   pcadv_rowmax_dgrad: dz_prev[r, :] = prev_act'(yprev[r, :]) * (*scale) * s[r] * w[idx[r], :]
+ *   pcadv_rowmax_wgrad: dw[idx[r], :] += s[r] * yprev[r, :];  dbias[idx[r]] += s[r]   (fp32)
+ * w is the pooled layer's [n, k] weight, yprev its [rows, k] input (k a multiple of 8). */
+int pcadv_rowmax_dgrad(const float* dy, const float* val, const int32_t* idx, int64_t rows, int32_t k,
+                       int32_t act, float slope, const float* scale, const void* w, int64_t ldw,
+                       int32_t w_dtype, const void* yprev, int64_t ld_y, int32_t y_dtype,
+                       int32_t prev_act, float prev_slope, void* dz, int64_t ld_dz, int32_t dz_dtype,
+                       void* stream);
+int pcadv_rowmax_wgrad(const float* dy, const float* val, const int32_t* idx, int64_t rows, int32_t n,
+                       int32_t k, int32_t act, float slope, const void* yprev, int64_t ld_y,
+                       int32_t y_dtype, float* dw, int64_t ld_dw, float* dbias, void* stream);
+
 /* scale2[0] = S = 2^floor(log2(target / max|x|)) (1 when x is all zero),
  * scale2[1] = 1 / S.  x is a [rows, cols] fp32 matrix with leading dimension ld.
  * `workspace` is one zero-filled uint32. */

@@ -83,6 +83,13 @@ def cases(P, N):
     w6 = r16((2048, 512), 0.05)
     _, key, _ = ops.linear([x5], w6, want_out=False, colmax=True, rows_per_group=N, engine=ENGINE_TC)
     g6, idx6 = ops.max_finalize(key, ACT_RELU)
+    # realistic argmax distribution (measured on the reference at xavier init, N = 4096: ~430
+    # touched rows per cloud, the hottest row the argmax of 100-150 channels)
+    pr = 1.0 / (torch.arange(432, device=DEV, dtype=torch.float32) + 6.0)
+    pick = torch.multinomial(pr.expand(B, -1), 2048, replacement=True)
+    rows_sel = torch.stack([torch.randperm(N, device=DEV)[:432] for _ in range(B)])
+    idx6 = torch.gather(rows_sel, 1, pick).to(torch.int32).contiguous()
+    g6 = g6.clamp_min(1e-3)
     dg6 = torch.randn((B, 2048), device=DEV)
     dw6 = torch.zeros((2048, 512), device=DEV)
     db6 = torch.zeros((2048,), device=DEV)
