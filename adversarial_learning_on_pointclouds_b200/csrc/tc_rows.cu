@@ -1,0 +1,559 @@
+// Tensor-core engine, forward / dgrad GEMMs with points on the MMA M axis.
+//
+//   tc_rows_kernel<act, out>: out[r, c] = epilogue(sum_k x[r, k] w[c, k]) for 128-row tiles.
+//
+// 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 =
+// epilogue.  The two 256-column TMEM accumulator buffers belong to the two epilogue *halves*
+// (warps 2..5 / 6..9): half h drains the CTA's tiles h, h+2, h+4, ... so two tiles are in the
+// epilogue at once while the MMA warp fills the next buffer.  Inside a half every warp owns a
+// TMEM lane quarter (32 rows) and works alone: it stages its 32 x 128-byte output slab in its
+// own shared-memory ring and one lane hands the slab to a TMA store; the activation-derivative
+// mask slab of the step arrives by TMA into the SAME slab and is overwritten in place by the
+// output.  No block-wide barrier exists in the steady state -- warps only meet when the staged
+// bias of their half changes.
+#include "tc_pipeline.cuh"
+
+namespace pcadv {
+namespace tc {
+
+constexpr int kRowsThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kWarpSlabBytes = 32 * 128;          // one warp's 32 rows x 128 B, 128B-swizzled
+constexpr int kMaxSlabs = 3;
+constexpr int kRowsMaxStages = 6;
+constexpr int kRowsBiasFloats = 2 * 3 * kMaxTileN;   // per half: bias + two per-cloud bias rows
+constexpr int kRowsSmemMax = 232448;              // 227 KB opt-in limit of sm_100
+
+struct RowsTail {
+  uint64_t full[kRowsMaxStages];
+  uint64_t empty[kRowsMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t mask_full[kEpiWarps][kMaxSlabs];
+  uint32_t tmem_base;
+};
+
+struct RowsParams {
+  int64_t rows;
+  int n;
+  int bn;                 // N-side tile (multiple of 16, <= 256)
+  int num_seg;
+  int seg_k[PCADV_MAX_SEG];
+  int64_t tiles_m, tiles_n;
+  uint32_t idesc;
+  int nstages, nslabs, stage_bytes;
+  // epilogue
+  const float* bias;
+  const float* group_bias;
+  int64_t rows_per_group;
+  const float* addend;
+  int64_t ld_addend;
+  float slope;
+  const void* mask;
+  int64_t ld_mask;
+  int mask_dtype, mask_act;
+  float mask_slope;
+  const float* out_scale;
+  void* out;
+  int64_t ld_out;
+  unsigned long long* rowmax_key;
+  int tma_out;            // output rows are TMA-storable: swizzled slab + tensor-map store
+  int tma_mask;           // mask slab fetched by TMA into the output slab (in place)
+  int compact_out;        // ld_out == n: a warp's 32 rows are one contiguous span (1-D bulk store)
+};
+
+struct RowsSmem {
+  uint8_t* stages;
+  uint8_t* epi;
+  float* bias;
+  RowsTail* tail;
+};
+
+__device__ __forceinline__ RowsSmem carve_rows(uint8_t* raw, const RowsParams& p) {
+  RowsSmem L;
+  L.stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  L.epi = L.stages + p.nstages * p.stage_bytes;
+  L.bias = reinterpret_cast<float*>(L.epi + kEpiWarps * p.nslabs * kWarpSlabBytes);
+  L.tail = reinterpret_cast<RowsTail*>(L.bias + kRowsBiasFloats);
+  return L;
+}
+
+static size_t rows_smem_bytes(int nstages, int stage_bytes, int nslabs) {
+  return 1024 + static_cast<size_t>(nstages) * stage_bytes + kEpiWarps * nslabs * kWarpSlabBytes +
+         kRowsBiasFloats * 4 + sizeof(RowsTail) + 16;
+}
+
+// 1-D bulk copy shared -> global (bytes and both addresses multiples of 16)
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void unpack16(const uint4 t4, int dtype, float* m) {
+  const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f;
+    if (dtype == PCADV_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+    else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+    m[2 * e] = f.x; m[2 * e + 1] = f.y;
+  }
+}
+
+// =====================================================================================
+// kAct: PCADV_ACT_*;  kOut: PCADV_F32 / PCADV_F16 / PCADV_BF16
+template <int kAct, int kOut>
+__global__ void __launch_bounds__(kRowsThreads, 1)
+tc_rows_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const RowsSmem L = carve_rows(smem_raw, p);
+  RowsTail* st = L.tail;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_seg; ++s) tma_prefetch_desc(&maps.act[s]);
+    tma_prefetch_desc(&maps.w);
+    if (p.tma_out) tma_prefetch_desc(&maps.out);
+    if (p.tma_mask) tma_prefetch_desc(&maps.mask);
+    for (int i = 0; i < kRowsMaxStages; ++i) {
+      mbar_init(&st->full[i], 1);
+      mbar_init(&st->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&st->tmem_full[i], 1);
+      mbar_init(&st->tmem_empty[i], 4);
+    }
+    for (int w = 0; w < kEpiWarps; ++w)
+      for (int i = 0; i < kMaxSlabs; ++i) mbar_init(&st->mask_full[w][i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&st->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = st->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t stage_tx = static_cast<uint32_t>((kTileM + p.bn) * kBlockK * 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int64_t tm = t / p.tiles_n, tn = t % p.tiles_n;
+        const int32_t m0 = static_cast<int32_t>(tm * kTileM);
+        const int32_t n0 = static_cast<int32_t>(tn * p.bn);
+        int kg = 0;
+        for (int s = 0; s < p.num_seg; ++s) {
+          for (int kk = 0; kk < p.seg_k[s]; kk += kBlockK, kg += kBlockK) {
+            mbar_wait_backoff(&st->empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&st->full[stage], stage_tx);
+            uint8_t* sa = L.stages + stage * p.stage_bytes;
+            tma_load_2d(sa, &maps.act[s], &st->full[stage], kk, m0);
+            tma_load_2d(sa + kABytes, &maps.w, &st->full[stage], kg, n0);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int total_chunks = 0;
+      for (int s = 0; s < p.num_seg; ++s) total_chunks += p.seg_k[s] / kBlockK;
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t buf_phase = 0;
+      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait_backoff(&st->tmem_empty[buf], buf_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kMaxTileN);
+        for (int c = 0; c < total_chunks; ++c) {
+          mbar_wait_backoff(&st->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(L.stages + stage * p.stage_bytes);
+          mma_chunk_kmajor(d_tmem, a_addr, a_addr + kABytes, p.idesc, c == 0);
+          umma_commit(&st->empty[stage]);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&st->tmem_full[buf]);
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: two halves x four lane quarters =================
+    const int ew = warp - 2;                              // 0..7
+    const int quarter = warp & 3;                         // TMEM lane quarter of this warp
+    const int half = ew >> 2;                             // which accumulator buffer / tile parity
+    const int lane_row = quarter * 32 + lane;             // row of the 128-row tile
+    const int hid = (ew & 3) * 32 + lane;                 // 0..127 inside the half
+    constexpr int kEsz = kOut == PCADV_F32 ? 4 : 2;
+    constexpr int kStepCols = 128 / kEsz;                 // columns per 128-byte slab row
+    constexpr int kChunks = kStepCols / 32;               // 32-column TMEM loads per step
+    const int steps = (p.bn + kStepCols - 1) / kStepCols;
+    const int S = p.nslabs;
+    uint8_t* myslabs = L.epi + ew * S * kWarpSlabBytes;
+    float* bias_s = L.bias + half * 3 * kMaxTileN;
+    float* gb_s = bias_s + kMaxTileN;                     // [2][kMaxTileN]
+    const float oscale = p.out_scale ? *p.out_scale : 1.f;
+    const float mneg = p.mask_act == PCADV_ACT_LEAKY ? p.mask_slope : 0.f;
+    const int64_t rpg = p.rows_per_group > 0 ? p.rows_per_group : p.rows;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);  // swizzle term of this thread's slab row
+
+    int slab = 0;                                         // ring position of the next step
+    uint32_t slab_par = 0;                                // parity of the slab's mask barrier
+    // mask prefetch iterator (lane 0): S - 1 steps ahead of the consumer
+    int64_t pf_t = blockIdx.x + static_cast<int64_t>(half) * gridDim.x;
+    int pf_step = 0, pf_slab = 0;
+    auto issue_mask = [&]() {
+      if (pf_t >= num_tiles) return;
+      const int64_t ptm = pf_t / p.tiles_n, ptn = pf_t % p.tiles_n;
+      uint64_t* bar = &st->mask_full[ew][pf_slab];
+      mbar_arrive_expect_tx(bar, kWarpSlabBytes);
+      tma_load_2d(myslabs + pf_slab * kWarpSlabBytes, &maps.mask, bar,
+                  static_cast<int32_t>(ptn * p.bn + pf_step * 64),
+                  static_cast<int32_t>(ptm * kTileM + quarter * 32));
+      if (++pf_slab == S) pf_slab = 0;
+      if (++pf_step == steps) { pf_step = 0; pf_t += 2 * static_cast<int64_t>(gridDim.x); }
+    };
+    if (p.tma_mask && lane == 0)
+      for (int i = 0; i < S - 1; ++i) issue_mask();
+
+    int staged_col = -1;
+    int64_t staged_g0 = -1, staged_g1 = -1;
+    uint32_t use = 0;
+    for (int64_t t = blockIdx.x + static_cast<int64_t>(half) * gridDim.x; t < num_tiles;
+         t += 2 * static_cast<int64_t>(gridDim.x), ++use) {
+      const int64_t tm = t / p.tiles_n, tn = t % p.tiles_n;
+      const int64_t r = tm * kTileM + lane_row;
+      const bool r_ok = r < p.rows;
+      const int col_base = static_cast<int>(tn * p.bn);
+      const int64_t row_first = tm * kTileM;
+      const int64_t row_last = row_first + kTileM - 1 < p.rows ? row_first + kTileM - 1 : p.rows - 1;
+      const int64_t g_first = row_first / rpg, g_last = row_last / rpg;
+      const int64_t g = r_ok ? r / rpg : g_first;
+      const bool gb_staged = p.group_bias != nullptr && (g_last - g_first) <= 1;
+
+      // ---- stage bias (and the tile's per-cloud bias rows) for this half; skipped while the
+      // staged values are still the ones the tile needs
+      const bool restage = col_base != staged_col ||
+                           (gb_staged && (g_first != staged_g0 || g_last != staged_g1));
+      if (restage) {
+        staged_col = col_base; staged_g0 = g_first; staged_g1 = g_last;
+        named_barrier_sync(1 + half, 128);               // previous tile's readers are done
+        for (int e = hid; e < kMaxTileN; e += 128) {
+          const int c = col_base + e;
+          const bool c_ok = e < p.bn && c < p.n;
+          bias_s[e] = c_ok ? (p.bias ? __ldg(p.bias + c) : 0.f) : (p.rowmax_key ? -INFINITY : 0.f);
+          if (gb_staged) {
+            gb_s[e] = c_ok ? __ldg(p.group_bias + g_first * p.n + c) : 0.f;
+            gb_s[kMaxTileN + e] = (c_ok && g_last != g_first) ? __ldg(p.group_bias + g_last * p.n + c) : 0.f;
+          }
+        }
+        named_barrier_sync(1 + half, 128);
+      }
+
+      mbar_wait(&st->tmem_full[half], use & 1);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                              static_cast<uint32_t>(half * kMaxTileN);
+      unsigned long long rkey = 0ull;
+      if (p.compact_out) {
+        // the warp's previous tile must have left the staging buffer
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+      }
+      for (int step = 0; step < steps; ++step) {
+        uint8_t* srow = myslabs + slab * kWarpSlabBytes + lane * 128;
+        if (p.tma_out) {
+          if (p.tma_mask) {
+            mbar_wait(&st->mask_full[ew][slab], slab_par);
+          } else {
+            // the store that last read this slab (S steps ago) is done with it
+            if (lane == 0) {
+              if (S == 2) bulk_wait_group_read<1>();
+              else bulk_wait_group_read<2>();
+            }
+            __syncwarp();
+          }
+        }
+        uint32_t raw[kChunks][32];
+#pragma unroll
+        for (int h = 0; h < kChunks; ++h)
+          if (step * kStepCols + h * 32 < p.bn) tmem_ld32_issue(taddr0 + step * kStepCols + h * 32, raw[h]);
+#pragma unroll
+        for (int h = 0; h < kChunks; ++h) tmem_ld32_wait(raw[h]);
+
+#pragma unroll
+        for (int h = 0; h < kChunks; ++h) {
+          const int c0 = step * kStepCols + h * 32;       // column inside the tile
+          if (c0 >= p.bn) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[h][j]);
+          const int cg = col_base + c0;
+          const int valid = p.n - cg < 32 ? (p.n - cg > 0 ? p.n - cg : 0) : 32;
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = b4[q];
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+          }
+          if (p.group_bias) {
+            if (gb_staged) {
+              const float4* g4 = reinterpret_cast<const float4*>(gb_s + (g != g_first ? kMaxTileN : 0) + c0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b = g4[q];
+                v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              }
+            } else if (r_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) v[j] += __ldg(p.group_bias + g * p.n + cg + j);
+            }
+          }
+          if (p.addend && r_ok) {
+            const float* ap = p.addend + r * p.ld_addend + cg;
+            if (valid == 32 && (reinterpret_cast<uintptr_t>(ap) & 15) == 0) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b = *reinterpret_cast<const float4*>(ap + 4 * q);
+                v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) v[j] += ap[j];
+            }
+          }
+          if (p.rowmax_key) {          // columns >= n carry -inf from bias_s and never win
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const unsigned long long k = pack_key(v[j], static_cast<uint32_t>(cg + j));
+              rkey = k > rkey ? k : rkey;
+            }
+          }
+          if (!p.out) continue;
+          if (kAct == PCADV_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (kAct == PCADV_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+          }
+          if (p.mask && p.mask_act != PCADV_ACT_NONE) {
+            if (p.tma_mask) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float m[8];
+                unpack16(*reinterpret_cast<const uint4*>(srow + (((h * 4 + q) ^ sw) << 4)), p.mask_dtype, m);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[q * 8 + e] = m[e] > 0.f ? v[q * 8 + e] : v[q * 8 + e] * mneg;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float m = (r_ok && j < valid) ? ld_as_float(p.mask, r * p.ld_mask + cg + j, p.mask_dtype) : 0.f;
+                v[j] = m > 0.f ? v[j] : v[j] * mneg;
+              }
+            }
+          }
+          if (p.out_scale) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= oscale;
+          }
+          if (p.tma_out) {
+            if (kOut == PCADV_F32) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(srow + ((static_cast<uint32_t>(q) ^ sw) << 4)) =
+                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                pk[j] = kOut == PCADV_F16 ? pack_f16x2_sat(v[2 * j], v[2 * j + 1])
+                                          : pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(srow + (((h * 4 + q) ^ sw) << 4)) =
+                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          } else if (p.compact_out) {
+            // row-compact staging: [32 rows][n] elements, the warp's rows are contiguous in HBM
+            uint8_t* crow = myslabs + static_cast<size_t>(lane) * p.n * kEsz + static_cast<size_t>(c0) * kEsz;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < valid) {
+                if (kOut == PCADV_F32) reinterpret_cast<float*>(crow)[j] = v[j];
+                else if (kOut == PCADV_F16) reinterpret_cast<__half*>(crow)[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+                else reinterpret_cast<__nv_bfloat16*>(crow)[j] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          } else if (r_ok && valid > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) st_from_float(p.out, r * p.ld_out + cg + j, kOut, v[j]);
+          }
+        }
+        if (p.tma_out) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&maps.out, myslabs + slab * kWarpSlabBytes, col_base + step * kStepCols,
+                         static_cast<int32_t>(tm * kTileM + quarter * 32));
+            bulk_commit_group();
+            if (p.tma_mask) {
+              // the slab filled next-but-(S-2) was last read by the store before this one
+              bulk_wait_group_read<1>();
+              issue_mask();
+            }
+          }
+          if (++slab == S) { slab = 0; slab_par ^= 1; }
+        }
+      }
+      if (p.compact_out && p.out) {
+        const int64_t wr0 = tm * kTileM + quarter * 32;   // first row of this warp
+        int64_t nrows = p.rows - wr0;
+        nrows = nrows > 32 ? 32 : nrows;
+        if (nrows > 0) {
+          const uint32_t bytes = static_cast<uint32_t>(nrows * p.n * kEsz);
+          uint8_t* gdst = reinterpret_cast<uint8_t*>(p.out) + wr0 * p.n * kEsz;
+          if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              bulk_store_1d(gdst, myslabs, bytes);
+              bulk_commit_group();
+            }
+          } else {
+            __syncwarp();
+            const uint32_t words = bytes / 4;             // n * esz * nrows; 16-bit n is even here
+            for (uint32_t i = lane; i < words; i += 32)
+              reinterpret_cast<uint32_t*>(gdst)[i] = reinterpret_cast<const uint32_t*>(myslabs)[i];
+            __syncwarp();
+          }
+        }
+      }
+      if (p.rowmax_key && r_ok && rkey) atomicMax(&p.rowmax_key[r], rkey);
+      // release the accumulator buffer of this half
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&st->tmem_empty[half]);
+    }
+    if (lane == 0) bulk_wait_group<0>();                  // all output slabs have landed
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef void (*RowsKernel)(const TensorMaps, const RowsParams);
+
+template <int kAct>
+static RowsKernel pick_out(int out_dtype) {
+  switch (out_dtype) {
+    case PCADV_F16: return tc_rows_kernel<kAct, PCADV_F16>;
+    case PCADV_BF16: return tc_rows_kernel<kAct, PCADV_BF16>;
+    default: return tc_rows_kernel<kAct, PCADV_F32>;
+  }
+}
+
+static RowsKernel pick_rows_kernel(int act, int out_dtype) {
+  switch (act) {
+    case PCADV_ACT_RELU: return pick_out<PCADV_ACT_RELU>(out_dtype);
+    case PCADV_ACT_LEAKY: return pick_out<PCADV_ACT_LEAKY>(out_dtype);
+    default: return pick_out<PCADV_ACT_NONE>(out_dtype);
+  }
+}
+
+static int ensure_rows_smem(const void* kernel) {
+  static const void* done[16] = {nullptr};
+  for (int i = 0; i < 16; ++i) {
+    if (done[i] == kernel) return 0;
+    if (done[i] == nullptr) {
+      PCADV_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kRowsSmemMax));
+      done[i] = kernel;
+      return 0;
+    }
+  }
+  return 0;
+}
+
+}  // namespace tc
+
+int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
+  using namespace tc;
+  const int dt = a.seg[0].dtype;
+  TensorMaps maps;
+  RowsParams p{};
+  p.rows = a.rows; p.n = a.n; p.num_seg = a.num_seg;
+  p.bn = (a.n + 15) / 16 * 16;
+  if (p.bn > kMaxTileN) p.bn = kMaxTileN;
+  int ktot = 0;
+  for (int i = 0; i < a.num_seg; ++i) {
+    PCADV_CHECK_ARG(a.seg[i].dtype == dt && a.seg[i].k % kBlockK == 0 &&
+                        tma_compatible(a.seg[i].ptr, dt, a.seg[i].ld),
+                    "tc_linear: segment %d not TMA-compatible (k=%d ld=%lld)", i, a.seg[i].k,
+                    (long long)a.seg[i].ld);
+    p.seg_k[i] = a.seg[i].k;
+    if (int rc = encode_tmap_2d(&maps.act[i], a.seg[i].ptr, dt, a.rows, a.seg[i].k, a.seg[i].ld,
+                                kBlockK, kTileM))
+      return rc;
+    ktot += a.seg[i].k;
+  }
+  PCADV_CHECK_ARG(tma_compatible(a.w, dt, a.ldw), "tc_linear: weight not TMA-compatible");
+  if (int rc = encode_tmap_2d(&maps.w, a.w, dt, a.n, ktot, a.ldw, kBlockK, p.bn)) return rc;
+  p.tiles_m = (a.rows + kTileM - 1) / kTileM;
+  p.tiles_n = (a.n + p.bn - 1) / p.bn;
+  p.idesc = make_idesc(kTileM, p.bn, dt == PCADV_BF16, false, false);
+  p.bias = a.bias; p.group_bias = a.group_bias; p.rows_per_group = a.rows_per_group;
+  p.addend = a.addend; p.ld_addend = a.ld_addend; p.slope = a.slope;
+  p.mask = a.mask; p.ld_mask = a.ld_mask; p.mask_dtype = a.mask_dtype; p.mask_act = a.mask_act;
+  p.mask_slope = a.mask_slope; p.out_scale = a.out_scale; p.out = a.out; p.ld_out = a.ld_out;
+  p.rowmax_key = a.rowmax_key;
+  const int out_dt = a.out ? a.out_dtype : PCADV_F16;
+  const int esz = out_dt == PCADV_F32 ? 4 : 2;
+  p.tma_out = (a.out && tma_compatible(a.out, out_dt, a.ld_out)) ? 1 : 0;
+  if (p.tma_out) {
+    if (int rc = encode_tmap_2d(&maps.out, a.out, out_dt, a.rows, a.n, a.ld_out, 128 / esz, 32))
+      return rc;
+  }
+  p.tma_mask = (p.tma_out && a.mask && a.mask_act != PCADV_ACT_NONE && out_dt != PCADV_F32 &&
+                a.mask_dtype != PCADV_F32 && tma_compatible(a.mask, a.mask_dtype, a.ld_mask)) ? 1 : 0;
+  if (p.tma_mask) {
+    if (int rc = encode_tmap_2d(&maps.mask, a.mask, a.mask_dtype, a.rows, a.n, a.ld_mask, 64, 32))
+      return rc;
+  }
+  p.nslabs = p.tma_mask ? 3 : 2;
+  // row-compact staging when rows are not TMA-storable but contiguous (fc4: 50 fp32 logits)
+  p.compact_out = (a.out && !p.tma_out && a.ld_out == a.n && p.tiles_n == 1 &&
+                   (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.n * esz) % 4 == 0 &&
+                   32 * a.n * esz <= p.nslabs * kWarpSlabBytes) ? 1 : 0;
+  p.stage_bytes = kABytes + p.bn * kBlockK * 2;
+  int nst = kRowsMaxStages;
+  while (nst > 2 && rows_smem_bytes(nst, p.stage_bytes, p.nslabs) > static_cast<size_t>(kRowsSmemMax)) --nst;
+  p.nstages = nst;
+  const size_t smem = rows_smem_bytes(p.nstages, p.stage_bytes, p.nslabs);
+  PCADV_CHECK_ARG(smem <= static_cast<size_t>(kRowsSmemMax), "tc_linear: shared memory budget exceeded");
+  const int64_t tiles = p.tiles_m * p.tiles_n;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  RowsKernel k = pick_rows_kernel(a.act, out_dt);
+  if (int rc = ensure_rows_smem(reinterpret_cast<const void*>(k))) return rc;
+  k<<<grid, kRowsThreads, smem, s>>>(maps, p);
+  PCADV_LAUNCHED();
+  return 0;
+}
+
+}  // namespace pcadv

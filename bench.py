@@ -326,7 +326,7 @@ def run_cuda(args):
         "gpu_launches": launches, "launch_mode": graph_note, "clocks": sampler.summary(),
         "roofline": roofline,
         "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in
-                               sorted(ksum.items(), key=lambda kv: -kv[1][1])[:12]},
+                               sorted(ksum.items(), key=lambda kv: -kv[1][1])[:args.top_kernels]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(args, N)
@@ -354,6 +354,7 @@ def main():
                     help="draw the smoothed GAN labels on the device instead of the CPU")
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--top-kernels", type=int, default=12)
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly")
     args = ap.parse_args()
     if args.impl == "reference":
