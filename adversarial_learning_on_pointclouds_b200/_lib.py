@@ -57,6 +57,19 @@ class MaxBwdArgs(C.Structure):
     ]
 
 
+class HeadArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("n", C.c_int32), ("mode", C.c_int32),
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("labels", C.c_void_p),
+        ("probs", C.c_void_p), ("ld_probs", C.c_int64), ("probs_dtype", C.c_int32),
+        ("probs_cols", C.c_int32),
+        ("dz", C.c_void_p), ("ld_dz", C.c_int64), ("dz_dtype", C.c_int32), ("dz_cols", C.c_int32),
+        ("dz_gain", C.c_float), ("loss_sum", C.c_void_p),
+    ]
+
+
+HEAD_CE, HEAD_LSM = 0, 1
+
 # every symbol include/pcadv.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pcadv_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
@@ -81,6 +94,10 @@ SYMBOLS = {
                                 C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "pcadv_convert_cm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pcadv_softmax_head": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
+    "pcadv_logsoftmax_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                       C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                       C.c_int32, C.c_void_p]),
     "pcadv_transpose": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pcadv_version": (C.c_int, []),

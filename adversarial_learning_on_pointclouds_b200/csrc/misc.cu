@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) maxbwd_rows_kernel(const pcadv_maxbwd_arg
   int* ends = sm_i;                                        // [rows_per_group]
   int* list = sm_i + a.rows_per_group;                     // [n] channels ordered by row
   float* dzv = reinterpret_cast<float*>(list + a.n);       // [n]
+  int* rowl = list + 2 * a.n;                              // [n] argmax row of every list entry
   __shared__ int part[256];
   const int g = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int N = static_cast<int>(a.rows_per_group);
@@ -196,15 +197,23 @@ __global__ void __launch_bounds__(256) maxbwd_rows_kernel(const pcadv_maxbwd_arg
   for (int r = lo; r < hi; ++r) { const int v = ends[r]; ends[r] = run; run += v; }
   __syncthreads();
   // fill: ends[r] walks from the row's start to its end
-  for (int c = t; c < a.n; c += 256)
-    if (dzv[c] != 0.f) list[atomicAdd(&ends[a.idx[static_cast<int64_t>(g) * a.n + c]], 1)] = c;
+  for (int c = t; c < a.n; c += 256) {
+    if (dzv[c] != 0.f) {
+      const int row = a.idx[static_cast<int64_t>(g) * a.n + c];
+      const int pos = atomicAdd(&ends[row], 1);
+      list[pos] = c;
+      rowl[pos] = row;
+    }
+  }
   __syncthreads();
-  // publish the bucket table: [ends (N) | list (n) | dz (n)] per cloud
-  int* ws = reinterpret_cast<int*>(a.workspace) + static_cast<int64_t>(g) * (N + 2 * a.n);
+  // publish the bucket table: [ends (N) | list (n) | dz (n) | row of list entry (n)] per cloud
+  int* ws = reinterpret_cast<int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
+  const int cnt = ends[N - 1];
   for (int r = t; r < N; r += 256) ws[r] = ends[r];
   for (int c = t; c < a.n; c += 256) {
     ws[N + c] = list[c];
     reinterpret_cast<float*>(ws + N + a.n)[c] = dzv[c];
+    ws[N + 2 * a.n + c] = c < cnt ? rowl[c] : -1;
   }
 }
 
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply_kernel(const pcadv_maxb
   const int64_t grow = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (grow >= static_cast<int64_t>(a.groups) * N) return;
   const int g = static_cast<int>(grow / N), r = static_cast<int>(grow - static_cast<int64_t>(g) * N);
-  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 2 * a.n);
+  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
   const int* ends = ws;
   const int* list = ws + N;
   const float* dzv = reinterpret_cast<const float*>(ws + N + a.n);
@@ -273,6 +282,200 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply_kernel(const pcadv_maxb
         st_pair(a.dz_inout, row * a.ld_dz + kk, a.dz_dtype, d);
       }
     }
+  }
+}
+
+// ---- 16-bit fast path of the apply step ----------------------------------------------------
+// Work item = kSegEntries consecutive entries of a cloud's row-sorted channel list; a warp owns
+// every run (equal argmax row) that STARTS inside its segment and follows it to its end, so no
+// row is touched by two warps and no atomics are needed, while a point that is the argmax of
+// hundreds of channels costs one warp a long run instead of serialising a whole cloud.  A lane
+// owns 8-element vectors lane + 32 j of the k-wide rows (16-byte gathers of w6 rows from L2).
+constexpr int kMaxVec = 4;        // k <= 1024
+constexpr int kSegEntries = 8;
+
+template <bool kBf16>
+__device__ __forceinline__ void fma8(const uint4 raw, float dz, float (&acc)[8]) {
+  const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f;
+    if (kBf16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+    else f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+    acc[2 * e] = fmaf(dz, f.x, acc[2 * e]);
+    acc[2 * e + 1] = fmaf(dz, f.y, acc[2 * e + 1]);
+  }
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_maxbwd_args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = static_cast<int>(a.rows_per_group);
+  const int segs = (a.n + kSegEntries - 1) / kSegEntries;
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (wid >= static_cast<int64_t>(a.groups) * segs) return;
+  const int g = static_cast<int>(wid / segs);
+  const int seg = static_cast<int>(wid - static_cast<int64_t>(g) * segs);
+  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
+  const int cnt = ws[N - 1];
+  const int* list = ws + N;
+  const float* dzv = reinterpret_cast<const float*>(ws + N + a.n);
+  const int* rowl = ws + N + 2 * a.n;
+  int q = seg * kSegEntries;
+  const int seg_end = q + kSegEntries < cnt ? q + kSegEntries : cnt;
+  if (q >= seg_end) return;
+  if (q > 0) {                         // skip the tail of a run that started in an earlier segment
+    const int prev = rowl[q - 1];
+    while (q < seg_end && rowl[q] == prev) ++q;
+    if (q >= seg_end) return;
+  }
+  const int nvec = a.k >> 3;
+  const uint4* wbase = reinterpret_cast<const uint4*>(a.w);
+  const int64_t ldw4 = a.ldw >> 3;
+  while (q < seg_end) {
+    const int row = rowl[q];
+    float acc[kMaxVec][8];
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+    bool more = true;
+    while (more) {
+      // metadata of the next 32 list entries, one per lane; the run is a prefix of the window
+      const int mq = q + lane;
+      int mrow = -1, mc = 0;
+      float mdz = 0.f;
+      if (mq < cnt) { mrow = rowl[mq]; mc = list[mq]; mdz = dzv[mc]; }
+      const unsigned same = __ballot_sync(0xffffffffu, mrow == row);
+      const int len = same == 0xffffffffu ? 32 : __ffs(~same) - 1;
+      more = len == 32;
+      for (int i = 0; i < len; i += 2) {
+        const int c0 = __shfl_sync(0xffffffffu, mc, i);
+        const float d0 = __shfl_sync(0xffffffffu, mdz, i);
+        const int i1 = i + 1 < len ? i + 1 : i;
+        const int c1 = __shfl_sync(0xffffffffu, mc, i1);
+        const float d1 = i + 1 < len ? __shfl_sync(0xffffffffu, mdz, i1) : 0.f;
+        uint4 r0[kMaxVec], r1[kMaxVec];
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+          const int v = lane + 32 * j;
+          if (v < nvec) {
+            r0[j] = __ldg(wbase + static_cast<int64_t>(c0) * ldw4 + v);
+            r1[j] = __ldg(wbase + static_cast<int64_t>(c1) * ldw4 + v);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+          if (lane + 32 * j < nvec) {
+            fma8<kBf16>(r0[j], d0, acc[j]);
+            fma8<kBf16>(r1[j], d1, acc[j]);
+          }
+        }
+      }
+      q += len;
+    }
+    // one read-modify-write of the touched row, through the previous layer's activation mask
+    const int64_t grow = static_cast<int64_t>(g) * a.rows_per_group + row;
+    const uint4* xrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.x) + grow * a.ldx);
+    uint4* drow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.dz_inout) + grow * a.ld_dz);
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nvec) {
+        const uint4 xr = xrow[v];
+        const uint4 dr = drow[v];
+        const uint32_t x4[4] = {xr.x, xr.y, xr.z, xr.w};
+        const uint32_t d4[4] = {dr.x, dr.y, dr.z, dr.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 xf, df;
+          if (kBf16) {
+            xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x4[e]));
+            df = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d4[e]));
+          } else {
+            xf = __half22float2(*reinterpret_cast<const __half2*>(&x4[e]));
+            df = __half22float2(*reinterpret_cast<const __half2*>(&d4[e]));
+          }
+          df.x += acc[j][2 * e] * act_grad_from_output(xf.x, a.prev_act, a.prev_slope);
+          df.y += acc[j][2 * e + 1] * act_grad_from_output(xf.y, a.prev_act, a.prev_slope);
+          o4[e] = kBf16 ? pack_bf16x2(df.x, df.y) : pack_f16x2_sat(df.x, df.y);
+        }
+        drow[v] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+}
+
+// dW / dbias, 16-bit x rows gathered with 16-byte loads: one CTA per channel c, 8 warps stride
+// over the clouds (four clouds per trip), no atomics.
+template <bool kBf16>
+__global__ void __launch_bounds__(256) maxbwd_dw16_kernel(const pcadv_maxbwd_args a) {
+  __shared__ float red[8][1024];
+  __shared__ float bred[8];
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = a.k >> 3;
+  float acc[kMaxVec][8];
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  float bsum = 0.f;
+  const uint4* xbase = reinterpret_cast<const uint4*>(a.x);
+  const int64_t ldx4 = a.ldx >> 3;
+  for (int g0 = warp; g0 < a.groups; g0 += 32) {
+    float dz[4];
+    int64_t r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + 8 * u;
+      dz[u] = 0.f;
+      r[u] = 0;
+      if (g < a.groups) {
+        const int64_t gc = static_cast<int64_t>(g) * a.n + c;
+        dz[u] = a.dg[gc] * act_grad_from_output(a.gval[gc], a.act, a.slope);
+        r[u] = static_cast<int64_t>(g) * a.rows_per_group + a.idx[gc];
+      }
+      bsum += dz[u];
+    }
+    if (a.dw) {
+#pragma unroll
+      for (int j = 0; j < kMaxVec; ++j) {
+        const int v = lane + 32 * j;
+        if (v < nvec) {
+          uint4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            x[u] = dz[u] != 0.f ? __ldg(xbase + r[u] * ldx4 + v) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) fma8<kBf16>(x[u], dz[u], acc[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][8 * v + e] = acc[j][e];
+    }
+  }
+  if (lane == 0) bred[warp] = bsum;
+  __syncthreads();
+  const float sc = a.scale ? *a.scale : 1.f;
+  if (a.dw) {
+    for (int k = threadIdx.x; k < a.k; k += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][k];
+      a.dw[static_cast<int64_t>(c) * a.ld_dw + k] += s * sc;
+    }
+  }
+  if (threadIdx.x == 0 && a.dbias) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += bred[w];
+    a.dbias[c] += s * sc;
   }
 }
 
@@ -504,7 +707,11 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
                     pair_ok(a->w, a->ldw, a->w_dtype) && pair_ok(a->dz_inout, a->ld_dz, a->dz_dtype);
   if (a->dw || a->dbias) {
     PCADV_CHECK_ARG(!a->dw || a->x, "pcadv_maxpool_bwd: dw needs x");
-    if (fast) maxbwd_dw_fast_kernel<<<a->n, 256, 0, s>>>(*a);
+    const bool x16 = a->x && a->x_dtype != PCADV_F32 && a->k % 8 == 0 && a->k <= 8 * 32 * kMaxVec &&
+                     a->ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0;
+    if (x16 && a->x_dtype == PCADV_BF16) maxbwd_dw16_kernel<true><<<a->n, 256, 0, s>>>(*a);
+    else if (x16) maxbwd_dw16_kernel<false><<<a->n, 256, 0, s>>>(*a);
+    else if (fast) maxbwd_dw_fast_kernel<<<a->n, 256, 0, s>>>(*a);
     else maxbwd_dw_kernel<<<a->n, 128, 0, s>>>(*a);
     PCADV_LAUNCHED();
   }
@@ -513,18 +720,31 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
     PCADV_CHECK_ARG(fast && a->rows_per_group <= 8192 && a->n <= 4096,
                     "pcadv_maxpool_bwd: dz_inout needs k %% 64 == 0, k <= 1024, rows_per_group <= 8192, "
                     "n <= 4096 (got k=%d rpg=%lld n=%d)", a->k, (long long)a->rows_per_group, a->n);
-    const size_t smem = (static_cast<size_t>(a->rows_per_group) + 2 * static_cast<size_t>(a->n)) * 4;
+    const size_t smem = (static_cast<size_t>(a->rows_per_group) + 3 * static_cast<size_t>(a->n)) * 4;
     static bool attr_done = false;
     if (!attr_done) {
       PCADV_CUDA_OK(cudaFuncSetAttribute(maxbwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (8192 + 2 * 4096) * 4));
+                                         (8192 + 3 * 4096) * 4));
       attr_done = true;
     }
     PCADV_CHECK_ARG(a->workspace != nullptr, "pcadv_maxpool_bwd: dz_inout needs a workspace");
     maxbwd_rows_kernel<<<a->groups, 256, smem, s>>>(*a);
     PCADV_LAUNCHED();
-    const int64_t total_rows = static_cast<int64_t>(a->groups) * a->rows_per_group;
-    maxbwd_rows_apply_kernel<<<static_cast<unsigned>((total_rows + 7) / 8), 256, 0, s>>>(*a);
+    auto vec_ok = [](const void* p, int64_t ld) {
+      return ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    };
+    const bool all16 = a->x_dtype != PCADV_F32 && a->w_dtype == a->x_dtype && a->dz_dtype == a->x_dtype &&
+                       a->k % 8 == 0 && vec_ok(a->x, a->ldx) && vec_ok(a->w, a->ldw) &&
+                       vec_ok(a->dz_inout, a->ld_dz);
+    if (all16) {
+      const int64_t items = static_cast<int64_t>(a->groups) * ((a->n + kSegEntries - 1) / kSegEntries);
+      const unsigned blocks = static_cast<unsigned>((items + 7) / 8);
+      if (a->x_dtype == PCADV_BF16) maxbwd_rows_apply16_kernel<true><<<blocks, 256, 0, s>>>(*a);
+      else maxbwd_rows_apply16_kernel<false><<<blocks, 256, 0, s>>>(*a);
+    } else {
+      const int64_t total_rows = static_cast<int64_t>(a->groups) * a->rows_per_group;
+      maxbwd_rows_apply_kernel<<<static_cast<unsigned>((total_rows + 7) / 8), 256, 0, s>>>(*a);
+    }
     PCADV_LAUNCHED();
   }
   if (a->dx_acc) {

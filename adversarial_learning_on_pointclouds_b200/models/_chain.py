@@ -110,13 +110,16 @@ def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0)
     return (dw[:n, :k] if need_w else None), (db[:n] if need_b else None)
 
 
-def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, scale2, addends=None):
+def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, scale2, addends=None,
+                   dx_packed=False):
     """Backward through a chain.  ``dz_last``: dz of the last layer ([rows, pad(n)]).
     ``need_w[i]`` / ``need_b[i]``: which parameter gradients to form (frozen
     discriminators skip wgrad, utils/trainer.py:885-886).  Returns
     (list of (dw, db), dx, dz0) where dx is the fp32, UNSCALED gradient of the chain
     input (only when ``need_x``; single input segment) and dz0 the (scaled) dz of
-    the first layer."""
+    the first layer.  With ``dx_packed`` dx keeps the scale and has the dtype and (padded)
+    width of the chain input instead."""
+    addends = addends or {}
     grads = [None] * len(layers)
     dz = dz_last
     for i in range(len(layers) - 1, -1, -1):
@@ -135,6 +138,12 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
         L = layers[0]
         k_in = L.w.shape[1]
         wt = dgrad_weight(prec, [L.w], k_in, [dz.shape[1]])
+        if dx_packed:
+            k_pad = x_segs[0].shape[1]
+            wt_p = wt.new_zeros((k_pad, wt.shape[1]))
+            wt_p[:k_in] = wt
+            dx, _, _ = ops.linear([dz], wt_p, out_dtype=prec.act_dtype, engine=prec.engine)
+            return grads, dx, dz
         if prec.scaled and k_in % 4:
             # pad the output width so its rows are 16-byte aligned (TMA store); slice afterwards
             k_pad = (k_in + 63) // 64 * 64

@@ -27,8 +27,12 @@ class MLPSpec:
     folded tiled-global-feature columns of models/pointnet.py:135-136).
     """
 
-    def __init__(self, acts, reduce=None, group=0, tap=None):
+    def __init__(self, acts, reduce=None, group=0, tap=None, box=None):
         self.acts, self.reduce, self.group, self.tap = list(acts), reduce, int(group), tap
+        # GradBox of a packed 16-bit input (models/_seg.py): the input gradient is then returned
+        # in the input's dtype, still carrying this backward's power-of-two scale, which is left
+        # in the box for the producer of the input
+        self.box = box
 
 
 class PointMLPFunction(torch.autograd.Function):
@@ -44,8 +48,14 @@ class PointMLPFunction(torch.autograd.Function):
         nl = len(spec.acts)
         layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
         ctx.bcn = None
+        ctx.packed_in = False
         x_in = None
-        if x.dim() == 3:
+        if x.dim() == 2 and prec.scaled and x.dtype == prec.act_dtype and x.shape[1] % 64 == 0 \
+                and x.stride(1) == 1 and x.stride(0) % 8 == 0:
+            # packed point-major 16-bit rows (the fused softmax heads' output): consumed as is
+            x_in = x
+            ctx.packed_in = True
+        elif x.dim() == 3:
             # B x C x N map (what the trainers hand the discriminators).  Channel-major memory
             # (torch softmax / log_softmax output) is transposed, converted and padded by one
             # kernel; a transposed view of point-major storage (the generator's logits) is free.
@@ -202,13 +212,14 @@ class PointMLPFunction(torch.autograd.Function):
             dz_t = ops.convert(addends.pop(t), prec.act_dtype, mask=ys[t], mask_act=P_.act,
                                mask_slope=P_.slope)
             g2, dx, dz0 = chain_backward(prec, dz_t, [x_in], ys[:t + 1], body[:t + 1],
-                                         need_w[:t + 1], need_b[:t + 1], need_x, scale2)
+                                         need_w[:t + 1], need_b[:t + 1], need_x, scale2,
+                                         dx_packed=ctx.packed_in)
             for i, gr in enumerate(g2):
                 grads[i] = gr
         elif body and dz_last is not None:
             g2, dx, dz0 = chain_backward(prec, dz_last, [x_in], ys[:len(body)], body,
                                          need_w[:len(body)], need_b[:len(body)], need_x, scale2,
-                                         addends=addends)
+                                         addends=addends, dx_packed=ctx.packed_in)
             for i, gr in enumerate(g2):
                 grads[i] = gr
         dgb = None
@@ -222,19 +233,24 @@ class PointMLPFunction(torch.autograd.Function):
             dw, db = grads[i] if grads[i] is not None else (None, None)
             flat.append(dw.reshape(params[2 * i].shape) if dw is not None else None)
             flat.append(db)
+        if ctx.packed_in and need_x:
+            if dx is None or dx.dtype != x_in.dtype or spec.box is None:
+                raise RuntimeError("a packed 16-bit input that requires grad needs a GradBox and a "
+                                   "layer chain in front of the reduction")
+            spec.box.scale2 = scale2
         if dx is not None and ctx.bcn is not None:
             B_, C_, N_ = ctx.bcn                                # back to B x C x N (a view)
             dx = dx.reshape(B_, N_, dx.shape[1])[:, :, :C_].transpose(1, 2)
         return (None, None, dx, dgb, *flat)
 
 
-def point_mlp(prec, x, layers, acts, reduce=None, group=0, tap=None, group_bias=None):
+def point_mlp(prec, x, layers, acts, reduce=None, group=0, tap=None, group_bias=None, box=None):
     """Convenience wrapper: ``layers`` are nn.Conv1d / nn.Linear modules or
     (weight, bias | None) pairs."""
     params = []
     for m in layers:
         params += [m.weight, m.bias] if hasattr(m, "weight") else [m[0], m[1]]
-    return PointMLPFunction.apply(prec, MLPSpec(acts, reduce, group, tap), x, group_bias, *params)
+    return PointMLPFunction.apply(prec, MLPSpec(acts, reduce, group, tap, box), x, group_bias, *params)
 
 
 class BmmFunction(torch.autograd.Function):

@@ -14,7 +14,7 @@ changes that leave the mathematics unchanged:
 import torch
 
 from .. import ops
-from ..ops import ACT_NONE, ACT_RELU, ENGINE_SIMT
+from ..ops import ACT_NONE, ACT_RELU, ENGINE_SIMT, HEAD_CE, HEAD_LSM
 from ._chain import (Layer, chain_forward, compute_weight, dgrad_weight, layer_wgrad, prepare_dz)
 
 _TRUNK = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
@@ -24,11 +24,38 @@ _SLICES = ((0, 64), (64, 192), (192, 320), (320, 448), (448, 960))   # x1..x5 in
 _G0, _G1, _C1 = 960, 3008, 3024                                       # global / class columns
 
 
+HEAD_GAIN = 256.0        # the fused CE head stores 256 * (softmax - onehot) as the 16-bit dz
+
+
+class GradBox:
+    """Side channel between the log-softmax head of the generator and the discriminator that
+    consumes its packed 16-bit output: the discriminator's backward leaves the power-of-two
+    scale of the gradient it returns here (``scale2`` = device tensor [S, 1/S])."""
+
+    __slots__ = ("scale2",)
+
+    def __init__(self):
+        self.scale2 = None
+
+
+def pad64(n):
+    return (n + 63) // 64 * 64
+
+
 class SegFunction(torch.autograd.Function):
-    """(pts [B,N,3], cls [B,1,16], *params) -> (logits [B,N,k] fp32, global [B,2048] fp32)."""
+    """(pts [B,N,3], cls [B,1,16], *params) -> (head output, global [B,2048] fp32).
+
+    head = "logits": logits [B,N,k] fp32 (models/pointnet.py:314-317).
+    head = "ce"    : (CrossEntropyLoss(pred, labels) as a 0-d tensor, softmax(pred) as a
+                     non-differentiable discriminator input) -- utils/trainer.py:899-901 in one
+                     pass over the logits; the loss gradient (softmax - onehot) is kept instead
+                     of the logits.
+    head = "lsm"   : log_softmax(pred) as a discriminator input -- utils/trainer.py:914.
+    Discriminator inputs are packed point-major [B, N, pad64(k)] 16-bit tensors in the 16-bit
+    precision modes and B x k x N fp32 views in the fp32 mode."""
 
     @staticmethod
-    def forward(ctx, prec, debug, pts, cls, *params):
+    def forward(ctx, prec, debug, head, labels, pts, cls, *params):
         if not pts.is_cuda:
             raise RuntimeError("PointNetSeg (libpcadv) needs CUDA tensors; there is no CPU path")
         p = dict(zip(PARAM_NAMES, params))
@@ -55,32 +82,101 @@ class SegFunction(torch.autograd.Function):
                                       Layer(W["fc4"], b["fc4"], ACT_NONE)],
                            final_fp32=True, rows_per_group=N, group_bias=cbias)
         logits = hs[3].view(B, N, -1)
-
-        ctx.prec, ctx.shape = prec, (B, N)
-        ctx.save_for_backward(pts2, cls2, g, idx, *xs, *hs[:3], *params)
+        k_out = logits.shape[2]
+        cols = pad64(k_out) if prec.scaled else k_out
+        ctx.prec, ctx.shape, ctx.head, ctx.box = prec, (B, N), head, None
+        if head == "logits":
+            out, extra, keep = logits, None, None
+        elif head == "ce":
+            loss_sum = torch.zeros(1, dtype=torch.float32, device=pts.device)
+            probs, u = ops.softmax_head(hs[3], HEAD_CE, labels=labels.reshape(-1).contiguous(),
+                                        out_dtype=prec.act_dtype, cols=cols, want_dz=True,
+                                        dz_gain=HEAD_GAIN if prec.scaled else 1.0, loss_sum=loss_sum)
+            out = loss_sum[0] / float(P)
+            extra = probs.view(B, N, cols) if prec.scaled else probs.view(B, N, k_out).transpose(1, 2)
+            keep = u
+        elif head == "lsm":
+            lp, _ = ops.softmax_head(hs[3], HEAD_LSM, out_dtype=prec.act_dtype, cols=cols)
+            out = lp.view(B, N, cols) if prec.scaled else lp.view(B, N, k_out).transpose(1, 2)
+            extra, keep = None, lp
+            ctx.box = GradBox()
+        else:
+            raise ValueError("head must be 'logits', 'ce' or 'lsm'")
+        ctx.has_keep = keep is not None
+        ctx.save_for_backward(pts2, cls2, g, idx, *xs, *hs[:3], *params, *([keep] if keep is not None else []))
         if debug is not None:
-            debug.update(x=xs, h=hs[:3], g=g, idx=idx, cbias=cbias)
-        return logits, g
+            debug.update(x=xs, h=hs[:3], g=g, idx=idx, cbias=cbias, logits=logits)
+        if head == "ce":
+            ctx.mark_non_differentiable(extra)
+            return out, extra, g
+        return out, g
 
     @staticmethod
-    def backward(ctx, dlogits, dg_ext):
+    def _head_dz(ctx, prec, keep, d_out, B, N, k_out, dev):
+        """(dz of fc4 [P, pad] in the chain's dtype, scale2 | None) from the head's gradient."""
+        P = B * N
+        if ctx.head == "ce":
+            if d_out is None:
+                d_out = torch.zeros((), dtype=torch.float32, device=dev)
+            d_out = d_out.float().reshape(())
+            if prec.scaled:
+                # dz_true = u * d_out / (GAIN * P): the kept u is the scaled dz with S = GAIN * P / d_out
+                inv = d_out / (HEAD_GAIN * P)
+                safe = torch.where(inv == 0, torch.ones_like(inv), inv)
+                return keep, torch.stack([1.0 / safe, inv])
+            return keep * (d_out / P), None
+        # "lsm": d_out is the gradient of the packed log-softmax map
+        if prec.scaled:
+            scale2 = ctx.box.scale2
+            ctx.box.scale2 = None
+            if d_out is None:
+                d_out = torch.zeros((P, keep.shape[1]), dtype=prec.act_dtype, device=dev)
+            d2 = d_out.reshape(P, -1)
+            if scale2 is None:
+                # gradient from a consumer that does not speak the GradBox protocol: unscaled
+                d2 = d2.float().contiguous()
+                scale2 = ops.amax_scale(d2)
+                return ops.logsoftmax_bwd(keep, d2, k_out, scale=scale2[0:1], out_dtype=prec.act_dtype,
+                                          cols=keep.shape[1]), scale2
+            if d2.stride(1) != 1:
+                d2 = d2.contiguous()
+            return ops.logsoftmax_bwd(keep, d2, k_out, out_dtype=prec.act_dtype, cols=keep.shape[1]), scale2
+        if d_out is None:
+            d_out = torch.zeros((B, k_out, N), dtype=torch.float32, device=dev)
+        d2 = d_out.transpose(1, 2).reshape(P, k_out)
+        if d2.stride(1) != 1 or d2.dtype != torch.float32:
+            d2 = d2.contiguous().float()
+        return ops.logsoftmax_bwd(keep, d2, k_out), None
+
+    @staticmethod
+    def backward(ctx, dlogits, *rest):
         prec = ctx.prec
         B, N = ctx.shape
         P = B * N
+        dg_ext = rest[-1]
         sv = ctx.saved_tensors
         pts2, cls2, g, idx = sv[0:4]
-        xs, hs, params = list(sv[4:9]), list(sv[9:12]), sv[12:]
+        xs, hs = list(sv[4:9]), list(sv[9:12])
+        keep = sv[-1] if ctx.has_keep else None
+        params = sv[12:-1] if ctx.has_keep else sv[12:]
         p = dict(zip(PARAM_NAMES, params))
-        need = dict(zip(PARAM_NAMES, ctx.needs_input_grad[4:]))
+        need = dict(zip(PARAM_NAMES, ctx.needs_input_grad[6:]))
         W = {n: p[n + ".weight"].reshape(p[n + ".weight"].shape[0], -1) for n in _TRUNK + _HEAD}
         dev = pts2.device
         k_out = W["fc4"].shape[0]
         grads = {}
 
-        if dlogits is None:
-            dlogits = torch.zeros((B, N, k_out), dtype=torch.float32, device=dev)
-        dl_cm = dlogits.transpose(1, 2)                               # B x k x N
-        if dlogits.stride(2) != 1 and dl_cm.is_contiguous() and ops.is_channel_major(dl_cm):
+        if ctx.head != "logits":
+            dz, scale2 = SegFunction._head_dz(ctx, prec, keep, dlogits, B, N, k_out, dev)
+            inv = scale2[1:2] if scale2 is not None else None
+            dl_cm = None
+        else:
+            if dlogits is None:
+                dlogits = torch.zeros((B, N, k_out), dtype=torch.float32, device=dev)
+            dl_cm = dlogits.transpose(1, 2)                           # B x k x N
+        if dl_cm is None:
+            pass
+        elif dlogits.stride(2) != 1 and dl_cm.is_contiguous() and ops.is_channel_major(dl_cm):
             # the trainer's CE / softmax backward hand the gradient over channel-major
             # (B x k x N contiguous): one kernel transposes, scales, converts and pads it
             scale2 = ops.amax_scale(dl_cm.reshape(B * k_out, N)) if prec.scaled else None
@@ -163,12 +259,12 @@ class SegFunction(torch.autograd.Function):
         grads["conv1.weight"], grads["conv1.bias"] = dw, db
 
         dpts = None
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[4]:
             wt = W["conv1"].t().contiguous()                          # [3, 64]
             dpts, _, _ = ops.linear([dz], wt, out_scale=inv, engine=ENGINE_SIMT)
             dpts = dpts.view(B, N, 3)
         dcls = None
-        if ctx.needs_input_grad[3]:
+        if ctx.needs_input_grad[5]:
             wc_t = W["fc1"][:, _G1:_C1].t().contiguous()              # [16, 256]
             dcls, _, _ = ops.linear([dcb], wc_t, out_scale=inv, engine=ENGINE_SIMT)
             dcls = dcls.view(B, 1, -1)
@@ -179,4 +275,4 @@ class SegFunction(torch.autograd.Function):
             if gr is not None:
                 gr = gr.reshape(p[n_].shape)
             out.append(gr)
-        return (None, None, dpts, dcls, *out)
+        return (None, None, None, None, dpts, dcls, *out)

@@ -26,9 +26,15 @@ def _prec(module):
 def _rows(x_bcn):
     """The B x C x N map is handed to PointMLPFunction as is: it reads channel-major
     memory (torch softmax output) and transposed views of point-major storage (the
-    generator's logits) without a torch-side copy."""
+    generator's logits) without a torch-side copy.  A 16-bit B x N x Cpad tensor is the
+    packed point-major map of the generator's fused softmax heads
+    (PointNetSeg.forward_ce / forward_logsoftmax) and goes in as [B*N, Cpad] rows.
+    Returns (rows, B, N, GradBox | None)."""
+    if x_bcn.dim() == 3 and x_bcn.dtype in (torch.float16, torch.bfloat16):
+        B, N, Cp = x_bcn.shape
+        return x_bcn.reshape(B * N, Cp), B, N, getattr(x_bcn, "_pcadv_box", None)
     B, C, N = x_bcn.shape
-    return x_bcn, B, N
+    return x_bcn, B, N, None
 
 
 class ConvDiscNet(nn.Module):
@@ -79,9 +85,9 @@ class PointwiseDiscNet(nn.Module):
         self.conv4 = torch.nn.Conv1d(64, 128, 1)
 
     def forward(self, x):
-        rows, B, N = _rows(x)
+        rows, B, N, box = _rows(x)
         y = point_mlp(_prec(self), rows, [self.conv1, self.conv2, self.conv3, self.conv4],
-                      [_RELU] * 4, reduce="channels")
+                      [_RELU] * 4, reduce="channels", box=box)
         return y.view(-1, self.input_pts)
 
 
@@ -99,8 +105,8 @@ class BaseDiscNet(nn.Module):
         self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
 
     def forward(self, x):
-        rows, B, N = _rows(x)
-        y = point_mlp(_prec(self), rows, [self.conv1, self.conv2, self.conv3], [_LEAKY] * 3)
+        rows, B, N, box = _rows(x)
+        y = point_mlp(_prec(self), rows, [self.conv1, self.conv2, self.conv3], [_LEAKY] * 3, box=box)
         return y.view(B, N, -1).transpose(1, 2)
 
 
@@ -116,7 +122,7 @@ class ShapeDiscNet(nn.Module):
         self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
 
     def forward(self, x):
-        rows, B, N = _rows(x)
+        rows, B, N, _ = _rows(x)
         prec = _prec(self)
         g = point_mlp(prec, rows, [self.conv], [_LEAKY], reduce="points", group=N)   # B x 512
         return point_mlp(prec, g, [self.fc1, self.fc2], [_LEAKY, _NONE])
@@ -134,7 +140,7 @@ class PointDiscNet(nn.Module):
         self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
 
     def forward(self, x):
-        rows, B, N = _rows(x)
+        rows, B, N, _ = _rows(x)
         y = point_mlp(_prec(self), rows, [self.conv1, self.conv2, self.conv3], [_LEAKY] * 3,
                       reduce="channels")
         return y.view(-1, self.input_pts)
@@ -160,10 +166,10 @@ class StackDiscNet(nn.Module):
         return out / (out + 1.0)
 
     def forward(self, x):
-        rows, B, N = _rows(x)
+        rows, B, N, box = _rows(x)
         prec = _prec(self)
         m = point_mlp(prec, rows, [self.conv1, self.conv2, self.conv3, self.conv4], [_LEAKY] * 4,
-                      reduce="channels")                                          # [B*N]
+                      reduce="channels", box=box)                                 # [B*N]
         s = point_mlp(prec, m.view(B * N, 1), [self.conv5], [_NONE])              # [B*N, S]
         shape_logits = s.view(B, N, -1).transpose(1, 2)                           # B x S x N
         return shape_logits, self.custom_activation(shape_logits)

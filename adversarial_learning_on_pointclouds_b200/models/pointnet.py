@@ -164,10 +164,30 @@ class PointNetSeg(nn.Module):
         self._debug = None                      # tests set a dict here to capture saved tensors
 
     def forward(self, x, cls):                  # B x N x 3, B x 1 x 16
-        logits, g = SegFunction.apply(_prec(self), self._debug, x, cls, *_params(self, _SEG_PARAMS))
+        logits, g = SegFunction.apply(_prec(self), self._debug, "logits", None, x, cls,
+                                      *_params(self, _SEG_PARAMS))
         # B x k x N as a transposed view of point-major storage, as the reference
         # returns it (:315); B x 2048 x 1
         return logits.transpose(1, 2), g.unsqueeze(2)
+
+    # ---- fused loss heads: the same forward with the trainer's softmax /
+    # log_softmax / CrossEntropyLoss (utils/trainer.py:899-901, :914) folded into one pass over
+    # the logits.  Optional: the reference-shaped forward() above stays the default.
+    def forward_ce(self, x, cls, seg):
+        """-> (CrossEntropyLoss(pred, seg) [0-d], softmax(pred) as a discriminator input,
+        global B x 2048 x 1).  ``seg``: B x N int64 part labels."""
+        loss, probs, g = SegFunction.apply(_prec(self), self._debug, "ce", seg, x, cls,
+                                           *_params(self, _SEG_PARAMS))
+        return loss, probs, g.unsqueeze(2)
+
+    def forward_logsoftmax(self, x, cls):
+        """-> (log_softmax(pred, dim=1) as a differentiable discriminator input, global)."""
+        lp, g = SegFunction.apply(_prec(self), self._debug, "lsm", None, x, cls,
+                                  *_params(self, _SEG_PARAMS))
+        node = lp.grad_fn
+        if node is not None and getattr(node, "box", None) is not None:
+            lp._pcadv_box = node.box
+        return lp, g.unsqueeze(2)
 
 
 class PointNetSeg_regulization(nn.Module):

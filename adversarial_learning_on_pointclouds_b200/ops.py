@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ENGINE_SIMT, ENGINE_TC, F16, F32, BF16)
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ENGINE_SIMT, ENGINE_TC, F16, F32, BF16, HEAD_CE, HEAD_LSM)
 
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -272,7 +272,7 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
     if dz_inout is not None:
         a.dz_inout, a.ld_dz, a.dz_dtype = _mat(dz_inout)
         a.prev_act, a.prev_slope = prev_act, float(prev_slope)
-        ws = torch.empty((groups * (int(rows_per_group) + 2 * n),), dtype=torch.int32, device=dg.device)
+        ws = torch.empty((groups * (int(rows_per_group) + 3 * n),), dtype=torch.int32, device=dg.device)
         a.workspace = _ptr(ws)
     a.scale = _f32(scale) if scale is not None else None
     _call("maxpool_bwd:n%d:k%d" % (n, a.k), _lib.lib().pcadv_maxpool_bwd, C.byref(a), _stream())
@@ -364,6 +364,49 @@ def convert_cm(x_bcn, out_dtype, cols_pad=None, scale=None):
     return dst
 
 
+def softmax_head(logits, mode, *, labels=None, out_dtype=torch.float32, cols=None, want_probs=True,
+                 want_dz=False, dz_gain=1.0, loss_sum=None):
+    """See ``pcadv_softmax_head``.  logits: fp32 [rows, n].  Returns (probs | None, dz | None): point-
+    major [rows, cols] matrices of ``out_dtype`` (softmax, or log_softmax in HEAD_LSM mode, and
+    dz_gain * (softmax - onehot)); ``loss_sum`` (fp32 scalar tensor) accumulates the CE sum."""
+    a = _lib.HeadArgs()
+    p, ld, dt = _mat(logits)
+    if dt != F32:
+        raise ValueError("softmax_head expects fp32 logits")
+    rows, n = logits.shape
+    cols = int(cols or n)
+    a.rows, a.n, a.mode, a.logits, a.ld = rows, n, mode, p, ld
+    if labels is not None:
+        if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != rows:
+            raise ValueError("labels must be a contiguous int64 tensor with one entry per row")
+        a.labels = _ptr(labels)
+    probs = dz = None
+    if want_probs:
+        probs = torch.empty((rows, cols), dtype=out_dtype, device=logits.device)
+        a.probs, a.ld_probs, a.probs_dtype, a.probs_cols = _ptr(probs), cols, _DT[out_dtype], cols
+    if want_dz:
+        dz = torch.empty((rows, cols), dtype=out_dtype, device=logits.device)
+        a.dz, a.ld_dz, a.dz_dtype, a.dz_cols = _ptr(dz), cols, _DT[out_dtype], cols
+    a.dz_gain = float(dz_gain)
+    a.loss_sum = _f32(loss_sum) if loss_sum is not None else None
+    _call("softmax_head:%s" % ("ce" if mode == _lib.HEAD_CE else "lsm"), _lib.lib().pcadv_softmax_head,
+          C.byref(a), _stream())
+    return probs, dz
+
+
+def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None):
+    """dz = scale * (dy - exp(lp) * rowsum(dy)) over the first ``n`` columns (see
+    ``pcadv_logsoftmax_bwd``); returns [rows, cols] of ``out_dtype`` (zero beyond n)."""
+    lpp, ld_lp, lpd = _mat(lp)
+    dyp, ld_dy, dyd = _mat(dy)
+    rows = lp.shape[0]
+    cols = int(cols or n)
+    dz = torch.empty((rows, cols), dtype=out_dtype, device=lp.device)
+    _call("logsoftmax_bwd", _lib.lib().pcadv_logsoftmax_bwd, lpp, lpd, ld_lp, dyp, dyd, ld_dy, rows, int(n),
+          _f32(scale) if scale is not None else None, _ptr(dz), _DT[out_dtype], cols, cols, _stream())
+    return dz
+
+
 def transpose(src, out_dtype=None):
     """dst[c, r] = src[r, c] (weight matrices only)."""
     p, ld, dt = _mat(src)
@@ -377,4 +420,5 @@ def transpose(src, out_dtype=None):
 
 __all__ = ["KernelTimer", "Precision", "set_default_precision", "default_precision", "linear", "wgrad",
            "max_finalize", "maxpool_bwd", "rowmax_bwd", "amax_scale", "convert", "transpose",
+           "softmax_head", "logsoftmax_bwd", "HEAD_CE", "HEAD_LSM",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ENGINE_SIMT", "ENGINE_TC"]

@@ -77,6 +77,58 @@ def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimize
     return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
 
 
+def adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
+                               batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
+                               device_labels=False, label_fn=None):
+    """The same iteration (utils/trainer.py:873-966) through the generator's fused loss heads
+    (SURVEY.md 8f rank 1): ``CrossEntropyLoss`` + ``softmax`` of the labelled pass and
+    ``log_softmax`` of the unlabelled pass are one kernel each over the logits, and the
+    discriminator reads their packed 16-bit output directly.  ``seg_loss`` must be
+    ``nn.CrossEntropyLoss()`` with default arguments (mean over all points); it is accepted only
+    to keep the signature of ``adversarial_seg_step``.  Same losses, same gradients."""
+    if not isinstance(seg_loss, torch.nn.CrossEntropyLoss) or seg_loss.weight is not None or \
+            seg_loss.reduction != "mean" or seg_loss.label_smoothing != 0.0:
+        raise ValueError("the fused step implements nn.CrossEntropyLoss() with default arguments")
+    gt_label, nogt_label = 1, 0
+    pool_gt = history_pool_gt or ImagePool(0)
+    pool_nogt = history_pool_nogt or ImagePool(0)
+
+    def label(d_out, value, random):
+        if label_fn is not None:
+            return label_fn(d_out, value, random)
+        if device_labels:
+            return _device_label(d_out, value, random)
+        return make_D_label(input=d_out, value=value, device=args.device, random=random)
+
+    model.train()
+    model_D.train()
+    optimizer.zero_grad()
+    optimizer_D.zero_grad()
+
+    for param in model_D.parameters():
+        param.requires_grad = False
+    pts, cls, seg = batch_gt
+    l_seg, pred_gt_softmax, _ = model.forward_ce(pts, cls, seg)          # :898-901
+    pts_nogt, cls_nogt = batch_nogt
+    pred_nogt_softmax, _ = model.forward_logsoftmax(pts_nogt, cls_nogt)   # :913-914
+    D_out = model_D(pred_nogt_softmax)
+    loss_adv = gan_loss(D_out, label(D_out, gt_label, False))
+    (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()
+
+    for param in model_D.parameters():
+        param.requires_grad = True
+    D_out = model_D(pool_gt.query(pred_gt_softmax.detach()))
+    loss_D_gt = gan_loss(D_out, label(D_out, gt_label, True)) * 0.5
+    loss_D_gt.backward()
+    D_out = model_D(pool_nogt.query(pred_nogt_softmax.detach()))
+    loss_D_nogt = gan_loss(D_out, label(D_out, nogt_label, True)) * 0.5
+    loss_D_nogt.backward()
+
+    optimizer.step()
+    optimizer_D.step()
+    return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
+
+
 class GraphedAdversarialSegStep:
     """``adversarial_seg_step`` captured once into a CUDA graph and replayed.
 
@@ -90,7 +142,7 @@ class GraphedAdversarialSegStep:
     """
 
     def __init__(self, model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, args, batch_gt,
-                 batch_nogt, warmup=3, device_labels=False):
+                 batch_nogt, warmup=3, device_labels=False, fused=False):
         self.static_gt = tuple(t.clone() for t in batch_gt)
         self.static_nogt = tuple(t.clone() for t in batch_nogt)
         self.device_labels = device_labels
@@ -112,9 +164,11 @@ class GraphedAdversarialSegStep:
                 return _device_label(d_out, value, True)
             return self.label_real if value == 1 else self.label_fake
 
+        step_fn = adversarial_seg_step_fused if fused else adversarial_seg_step
+
         def run():
-            return adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D,
-                                        self.static_gt, self.static_nogt, args, label_fn=label_fn)
+            return step_fn(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D,
+                           self.static_gt, self.static_nogt, args, label_fn=label_fn)
 
         self._draw_labels(0)
         self._upload_labels()

@@ -185,6 +185,7 @@ def run_cuda(args):
     from adversarial_learning_on_pointclouds_b200 import models as M, ops, Precision
     from adversarial_learning_on_pointclouds_b200.utils import init_net
     from adversarial_learning_on_pointclouds_b200.trainer import (adversarial_seg_step,
+                                                                  adversarial_seg_step_fused,
                                                                   GraphedAdversarialSegStep)
     from adversarial_learning_on_pointclouds_b200.parallel import DistributedOptimizer
 
@@ -218,9 +219,12 @@ def run_cuda(args):
     dev_nogt = tuple(t.to(dev) for t in host_nogt)
     loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
+    fused = not args.no_fused
+    step_fn = adversarial_seg_step_fused if fused else adversarial_seg_step
+
     def step(bg, bn):
-        return adversarial_seg_step(g, d, gan_loss, seg_loss, opt, optD, bg, bn, targs,
-                                    device_labels=args.device_labels)
+        return step_fn(g, d, gan_loss, seg_loss, opt, optD, bg, bn, targs,
+                       device_labels=args.device_labels)
 
     def barrier():
         if world > 1:
@@ -254,7 +258,8 @@ def run_cuda(args):
     if use_graph:
         try:
             gstep = GraphedAdversarialSegStep(g, d, gan_loss, seg_loss, opt, optD, targs, dev_gt,
-                                              dev_nogt, warmup=1, device_labels=args.device_labels)
+                                              dev_nogt, warmup=1, device_labels=args.device_labels,
+                                              fused=fused)
             graph_note = "whole step replayed from one CUDA graph (%d libpcadv launches per step)" \
                 % gstep.launches_per_step
             launches = gstep.launches_per_step * args.steps
@@ -323,7 +328,11 @@ def run_cuda(args):
         "data": "synthetic", "config": workload_config(args.workload, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "launch_mode": graph_note, "clocks": sampler.summary(),
+        "gpu_launches": launches, "launch_mode": graph_note,
+        "step_api": ("fused loss heads (PointNetSeg.forward_ce / forward_logsoftmax, "
+                     "trainer.adversarial_seg_step_fused)" if fused else
+                     "reference-shaped modules + torch losses (trainer.adversarial_seg_step)"),
+        "clocks": sampler.summary(),
         "roofline": roofline,
         "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in
                                sorted(ksum.items(), key=lambda kv: -kv[1][1])[:args.top_kernels]},
@@ -355,6 +364,9 @@ def main():
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--top-kernels", type=int, default=12)
+    ap.add_argument("--no-fused", action="store_true",
+                    help="run the loop body on the reference-shaped forward() + torch softmax / CE "
+                         "instead of the fused loss heads")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -158,7 +158,7 @@ typedef struct pcadv_maxbwd_args {
   int32_t dz_dtype;
   void* dz_inout;             /* [rows, k] or NULL */
   int64_t ld_dz;
-  void* workspace;            /* with dz_inout: >= groups * (rows_per_group + 2 * n) * 4 bytes */
+  void* workspace;            /* with dz_inout: >= groups * (rows_per_group + 3 * n) * 4 bytes */
   int64_t rows_per_group;
   const float* dg;            /* [groups, n] */
   const float* gval;          /* [groups, n] pooled post-activation value */
@@ -217,6 +217,48 @@ int pcadv_convert(const void* src, int32_t src_dtype, int64_t ld_src, int64_t ro
 int pcadv_convert_cm(const float* src, int64_t batch_stride, int64_t chan_stride, int64_t groups,
                      int64_t rows_per_group, int32_t cols, void* dst, int32_t dst_dtype,
                      int64_t ld_dst, int32_t cols_pad, const float* scale, void* stream);
+
+/*
+ * pcadv_softmax_head: one pass over the fp32 segmentation logits [rows, n] (n <= 128):
+ *   mode PCADV_HEAD_CE  (labelled batch, utils/trainer.py:899-901)
+ *     probs[r, c]  = softmax(logits[r, :])[c]                       F.softmax(pred, dim=1)
+ *     dz[r, c]     = dz_gain * (probs[r, c] - [c == labels[r]])     d CrossEntropyLoss / d logits,
+ *                                                                   up to the 1 / rows mean factor
+ *     *loss_sum   += sum_r (logsumexp(logits[r, :]) - logits[r, labels[r]])
+ *   mode PCADV_HEAD_LSM (unlabelled batch, utils/trainer.py:914)
+ *     probs[r, c]  = log_softmax(logits[r, :])[c]
+ * probs / dz are point-major [rows, *_cols] matrices of *_dtype, zero-filled in the columns
+ * n <= c < *_cols (the K padding the discriminator's / fc4-dgrad's tensor-core GEMM wants).
+ * Any of probs, dz, loss_sum may be NULL.
+ */
+enum { PCADV_HEAD_CE = 0, PCADV_HEAD_LSM = 1 };
+typedef struct pcadv_head_args {
+  int64_t rows;
+  int32_t n;
+  int32_t mode;
+  const float* logits;
+  int64_t ld;
+  const int64_t* labels;      /* [rows] or NULL */
+  void* probs;
+  int64_t ld_probs;
+  int32_t probs_dtype;
+  int32_t probs_cols;
+  void* dz;
+  int64_t ld_dz;
+  int32_t dz_dtype;
+  int32_t dz_cols;
+  float dz_gain;
+  float* loss_sum;            /* device scalar, accumulated into, or NULL */
+} pcadv_head_args;
+
+int pcadv_softmax_head(const pcadv_head_args* a, void* stream);
+
+/* Backward of log_softmax over the columns (utils/trainer.py:914 under :927-929):
+ *   dz[r, c] = (*scale) * (dy[r, c] - exp(lp[r, c]) * sum_j dy[r, j]),  c < n;  0 for n <= c < dz_cols.
+ * lp is the saved log_softmax output, dy its incoming gradient; any float dtype each. */
+int pcadv_logsoftmax_bwd(const void* lp, int32_t lp_dtype, int64_t ld_lp, const void* dy,
+                         int32_t dy_dtype, int64_t ld_dy, int64_t rows, int32_t n, const float* scale,
+                         void* dz, int32_t dz_dtype, int64_t ld_dz, int32_t dz_cols, void* stream);
 
 /* dst[c, r] = src[r, c] with conversion: builds the [k, n] copy of a weight
  * matrix that dgrad consumes. */

@@ -409,6 +409,98 @@ def test_adversarial_step_vs_oracle_step(mode):
         assert rel_err(v.grad, gp[k].grad) < loose, k
 
 
+# ------------------------------------------------------------- fused loss heads
+@pytest.mark.parametrize("out_dtype,cols", [(torch.float32, 50), (torch.float16, 64), (torch.bfloat16, 64)])
+@pytest.mark.parametrize("rows", [1, 77, 4096 + 5])
+def test_softmax_head_kernels(out_dtype, cols, rows):
+    """pcadv_softmax_head / pcadv_logsoftmax_bwd against torch (fp64) on the same logits."""
+    n = 50
+    logits = (_rand((rows, n), 5) * 3).to(DEV)
+    labels = torch.randint(0, n, (rows,), generator=torch.Generator().manual_seed(6)).to(DEV)
+    ref = logits.double()
+    tol = 2e-6 if out_dtype == torch.float32 else (2e-3 if out_dtype == torch.float16 else 1.6e-2)
+    loss_sum = torch.zeros(1, device=DEV)
+    probs, dz = ops.softmax_head(logits, ops.HEAD_CE, labels=labels, out_dtype=out_dtype, cols=cols,
+                                 want_dz=True, dz_gain=4.0, loss_sum=loss_sum)
+    sm = torch.softmax(ref, 1)
+    assert rel_err(probs[:, :n], sm) < tol
+    assert rel_err(dz[:, :n], 4.0 * (sm - F.one_hot(labels, n).double())) < tol
+    assert probs[:, n:].abs().max().item() == 0 if cols > n else True
+    assert dz[:, n:].abs().max().item() == 0 if cols > n else True
+    ce = F.cross_entropy(ref, labels, reduction="sum").item()
+    assert abs(loss_sum.item() - ce) <= 2e-6 * abs(ce) + 1e-6
+    lp, none = ops.softmax_head(logits, ops.HEAD_LSM, out_dtype=out_dtype, cols=cols)
+    assert none is None
+    assert rel_err(lp[:, :n], torch.log_softmax(ref, 1)) < tol
+    # log_softmax backward from the saved (rounded) lp and a random incoming gradient
+    dy = _rand((rows, cols), 7).to(DEV).to(out_dtype)
+    dy[:, n:] = 0
+    sc = torch.tensor([0.5], device=DEV)
+    got = ops.logsoftmax_bwd(lp, dy, n, scale=sc, out_dtype=out_dtype, cols=cols)
+    lpd, dyd = lp[:, :n].double(), dy[:, :n].double()
+    want = 0.5 * (dyd - lpd.exp() * dyd.sum(1, keepdim=True))
+    assert rel_err(got[:, :n], want) < tol
+    if cols > n:
+        assert got[:, n:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_fused_adversarial_step_vs_oracle_step(mode):
+    """trainer.adversarial_seg_step_fused (fused CE / softmax / log_softmax heads, packed
+    16-bit discriminator inputs) against oracle.steps: same losses, same gradients."""
+    from adversarial_learning_on_pointclouds_b200.trainer import adversarial_seg_step_fused
+    import argparse
+    torch.manual_seed(1)
+    g = init_net(M.PointNetSeg(50), "cpu", "xavier")
+    d = init_net(M.PointwiseDiscNet(384, 50), "cpu", "xavier")
+    randomize_biases([g, d], 3)
+    gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
+    g.to(DEV); d.to(DEV)
+    g.precision = d.precision = Precision(mode)
+    pts, _, seg, cls = inputs(3, 384, 8)
+    pts2, _, _, cls2 = inputs(3, 384, 9)
+    opt = torch.optim.SGD(g.parameters(), lr=0.0)
+    optD = torch.optim.SGD(d.parameters(), lr=0.0)
+    targs = argparse.Namespace(device=DEV, lambda_seg=1.0, lambda_adv=0.5)
+    torch.manual_seed(77)
+    l_seg, l_adv, l_D = adversarial_seg_step_fused(
+        g, d, torch.nn.BCEWithLogitsLoss(), torch.nn.CrossEntropyLoss(), opt, optD,
+        tuple(t.to(DEV) for t in (pts, cls, seg)), tuple(t.to(DEV) for t in (pts2, cls2)), targs)
+    torch.manual_seed(77)
+    ref = steps.adversarial_seg_step(gp, dp, (pts, cls, seg), (pts2, cls2), lambda_adv=0.5)
+    tol = TOL[mode]
+    assert abs(l_seg.item() - ref["l_seg"]) < 10 * tol and abs(l_adv.item() - ref["l_adv"]) < 10 * tol
+    loose = max(50 * tol, 5e-3)
+    for k, v in d.named_parameters():
+        assert rel_err(v.grad, dp[k].grad) < loose, k
+    for k, v in g.named_parameters():
+        assert rel_err(v.grad, gp[k].grad) < loose, k
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_fused_heads_match_reference_shaped_forward(mode):
+    """forward_ce / forward_logsoftmax against forward() + torch losses on the same module:
+    loss, discriminator inputs and generator gradients."""
+    g = build_seg(11, 12).to(DEV)
+    g.precision = Precision(mode)
+    pts, _, seg, cls = inputs(2, 300, 21)
+    pts, seg, cls = pts.to(DEV), seg.to(DEV), cls.to(DEV)
+    tol = TOL[mode]
+    pred, _ = g(pts, cls)
+    l_ref = F.cross_entropy(pred, seg)
+    g.zero_grad(); (3.0 * l_ref).backward()
+    ref_grads = {k: v.grad.clone() for k, v in g.named_parameters()}
+    loss, probs, glob = g.forward_ce(pts, cls, seg)
+    g.zero_grad(); (3.0 * loss).backward()
+    assert abs(loss.item() - l_ref.item()) < 10 * tol
+    sm = F.softmax(pred.detach(), dim=1)                                  # B x 50 x N
+    got = probs[:, :, :50].transpose(1, 2) if probs.dtype != torch.float32 else probs
+    assert rel_err(got, sm) < max(tol, 2e-3 if mode != "fp32" else tol)
+    assert not probs.requires_grad
+    for k, v in g.named_parameters():
+        assert rel_err(v.grad, ref_grads[k]) < max(20 * tol, 2e-3 if mode != "fp32" else 0), k
+
+
 def test_launch_counter_counts():
     before = pkg._lib.launch_count()
     x = _rand((256, 64), 1)
