@@ -31,6 +31,8 @@ class LinearArgs(C.Structure):
         ("mask_act", C.c_int32), ("mask_slope", C.c_float), ("out_dtype", C.c_int32),
         ("out_scale", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64),
         ("colmax_key", C.c_void_p), ("rowmax_key", C.c_void_p),
+        ("bits_out", C.c_void_p), ("ld_bits_out", C.c_int64),
+        ("mask_bits", C.c_void_p), ("ld_mask_bits", C.c_int64),
     ]
 
 

@@ -23,6 +23,8 @@ constexpr int kMaxSlabs = 3;
 constexpr int kRowsMaxStages = 6;
 constexpr int kRowsBiasFloats = 2 * 3 * kMaxTileN;   // per half: bias + two per-cloud bias rows
 constexpr int kRowsSmemMax = 232448;              // 227 KB opt-in limit of sm_100
+constexpr int kBitsWords = kMaxTileN / 32;        // sign-bit words per tile row
+constexpr int kBitsBytes = kEpiWarps * 32 * kBitsWords * 4;   // per-warp [32 rows][8 words] staging
 
 struct RowsTail {
   uint64_t full[kRowsMaxStages];
@@ -60,12 +62,17 @@ struct RowsParams {
   int tma_out;            // output rows are TMA-storable: swizzled slab + tensor-map store
   int tma_mask;           // mask slab fetched by TMA into the output slab (in place)
   int compact_out;        // ld_out == n: a warp's 32 rows are one contiguous span (1-D bulk store)
+  uint32_t* bits_out;     // [rows, ld_bits_out] sign bits of the stored output (n % 64 == 0)
+  int64_t ld_bits_out;
+  const uint32_t* mask_bits;   // 1-bit form of the mask
+  int64_t ld_mask_bits;
 };
 
 struct RowsSmem {
   uint8_t* stages;
   uint8_t* epi;
   float* bias;
+  uint32_t* bits;
   RowsTail* tail;
 };
 
@@ -74,13 +81,14 @@ __device__ __forceinline__ RowsSmem carve_rows(uint8_t* raw, const RowsParams& p
   L.stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   L.epi = L.stages + p.nstages * p.stage_bytes;
   L.bias = reinterpret_cast<float*>(L.epi + kEpiWarps * p.nslabs * kWarpSlabBytes);
-  L.tail = reinterpret_cast<RowsTail*>(L.bias + kRowsBiasFloats);
+  L.bits = reinterpret_cast<uint32_t*>(L.bias + kRowsBiasFloats);
+  L.tail = reinterpret_cast<RowsTail*>(reinterpret_cast<uint8_t*>(L.bits) + kBitsBytes);
   return L;
 }
 
 static size_t rows_smem_bytes(int nstages, int stage_bytes, int nslabs) {
   return 1024 + static_cast<size_t>(nstages) * stage_bytes + kEpiWarps * nslabs * kWarpSlabBytes +
-         kRowsBiasFloats * 4 + sizeof(RowsTail) + 16;
+         kRowsBiasFloats * 4 + kBitsBytes + sizeof(RowsTail) + 16;
 }
 
 // 1-D bulk copy shared -> global (bytes and both addresses multiples of 16)
@@ -101,18 +109,9 @@ __device__ __forceinline__ void unpack16(const uint4 t4, int dtype, float* m) {
   }
 }
 
-// =====================================================================================
-// kAct: PCADV_ACT_*;  kOut: PCADV_F32 / PCADV_F16 / PCADV_BF16
-template <int kAct, int kOut>
-__global__ void __launch_bounds__(kRowsThreads, 1)
-tc_rows_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const RowsSmem L = carve_rows(smem_raw, p);
-  RowsTail* st = L.tail;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t num_tiles = p.tiles_m * p.tiles_n;
-
+// ---- roles shared by the general and the lean kernel -------------------------------------------
+__device__ __forceinline__ uint32_t rows_setup(const TensorMaps& maps, const RowsParams& p, RowsTail* st,
+                                               int warp, int lane) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_seg; ++s) tma_prefetch_desc(&maps.act[s]);
     tma_prefetch_desc(&maps.w);
@@ -134,56 +133,333 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = st->tmem_base;
+  return st->tmem_base;
+}
+
+__device__ __forceinline__ void rows_producer(const TensorMaps& maps, const RowsParams& p,
+                                              const RowsSmem& L, RowsTail* st, int64_t num_tiles) {
+  const uint32_t stage_tx = static_cast<uint32_t>((kTileM + p.bn) * kBlockK * 2);
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int64_t tm = t / p.tiles_n, tn = t % p.tiles_n;
+    const int32_t m0 = static_cast<int32_t>(tm * kTileM);
+    const int32_t n0 = static_cast<int32_t>(tn * p.bn);
+    int kg = 0;
+    for (int s = 0; s < p.num_seg; ++s) {
+      for (int kk = 0; kk < p.seg_k[s]; kk += kBlockK, kg += kBlockK) {
+        mbar_wait_backoff(&st->empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&st->full[stage], stage_tx);
+        uint8_t* sa = L.stages + stage * p.stage_bytes;
+        tma_load_2d(sa, &maps.act[s], &st->full[stage], kk, m0);
+        tma_load_2d(sa + kABytes, &maps.w, &st->full[stage], kg, n0);
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void rows_mma(const RowsParams& p, const RowsSmem& L, RowsTail* st,
+                                         uint32_t tmem_base, int64_t num_tiles) {
+  int total_chunks = 0;
+  for (int s = 0; s < p.num_seg; ++s) total_chunks += p.seg_k[s] / kBlockK;
+  int stage = 0;
+  uint32_t phase = 0;
+  int buf = 0;
+  uint32_t buf_phase = 0;
+  for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    mbar_wait_backoff(&st->tmem_empty[buf], buf_phase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kMaxTileN);
+    for (int c = 0; c < total_chunks; ++c) {
+      mbar_wait_backoff(&st->full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(L.stages + stage * p.stage_bytes);
+      mma_chunk_kmajor(d_tmem, a_addr, a_addr + kABytes, p.idesc, c == 0);
+      umma_commit(&st->empty[stage]);
+      if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(&st->tmem_full[buf]);
+    if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+  }
+}
+
+__device__ __forceinline__ void rows_teardown(int warp, uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// explicit shared-space accesses (the epilogue's pointers are carved from one dynamic buffer and
+// would otherwise compile to generic LD / ST)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tma_store_2d_addr(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ---- sign-bit maps -----------------------------------------------------------------------------
+// Word w of a row covers columns 32 w .. 32 w + 31; column 2 k sits at bit k, column 2 k + 1 at bit
+// 16 + k (k = 0..15): the two halves of packed 16-bit pair k map to the two halves of the word, so
+// one HSET2 + one LOP3 per pair builds it and one LOP3 + one FSEL per element applies it.
+template <int kOut>
+__device__ __forceinline__ uint32_t pair_gt0_mask(uint32_t packed) {
+  // 0xffff in each half whose 16-bit value is > 0
+  uint32_t m;
+  if (kOut == PCADV_F16) asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(packed), "r"(0u));
+  else asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(packed), "r"(0u));
+  return m;
+}
+
+constexpr int kAddNone = 0, kAddBias = 1, kAddBiasGroup = 2;
+
+// =====================================================================================
+// Lean variant for the layers that dominate the step: 16-bit TMA-stored output, n % 64 == 0, no
+// addend / row-max / output scale.  kAdd: what is added to the accumulator (nothing -- dgrad;
+// bias -- forward layers; bias + per-cloud bias -- fc1).  kMaskBits: multiply by act'(.) read from
+// the forward layer's sign-bit map (dgrad).  Emits the sign-bit map of its own output on request.
+template <int kAct, int kOut, int kAdd, bool kMaskBits>
+__global__ void __launch_bounds__(kRowsThreads, 1)
+tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const RowsSmem L = carve_rows(smem_raw, p);
+  RowsTail* st = L.tail;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t num_tiles = p.tiles_m * p.tiles_n;
+  const uint32_t tmem_base = rows_setup(maps, p, st, warp, lane);
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      const uint32_t stage_tx = static_cast<uint32_t>((kTileM + p.bn) * kBlockK * 2);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int64_t tm = t / p.tiles_n, tn = t % p.tiles_n;
-        const int32_t m0 = static_cast<int32_t>(tm * kTileM);
-        const int32_t n0 = static_cast<int32_t>(tn * p.bn);
-        int kg = 0;
-        for (int s = 0; s < p.num_seg; ++s) {
-          for (int kk = 0; kk < p.seg_k[s]; kk += kBlockK, kg += kBlockK) {
-            mbar_wait_backoff(&st->empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&st->full[stage], stage_tx);
-            uint8_t* sa = L.stages + stage * p.stage_bytes;
-            tma_load_2d(sa, &maps.act[s], &st->full[stage], kk, m0);
-            tma_load_2d(sa + kABytes, &maps.w, &st->full[stage], kg, n0);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+    if (lane == 0) rows_producer(maps, p, L, st, num_tiles);
+  } else if (warp == 1) {
+    if (lane == 0) rows_mma(p, L, st, tmem_base, num_tiles);
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int lane_row = quarter * 32 + lane;
+    const int hid = (ew & 3) * 32 + lane;
+    const int steps = p.bn >> 6;                          // bn is a multiple of 64 here
+    const int tiles_n = static_cast<int>(p.tiles_n);
+    const int n = p.n, bn = p.bn;
+    const uint32_t slab0 = smem_u32(L.epi + ew * 2 * kWarpSlabBytes) + lane * 128;   // two slabs
+    const uint32_t slab_tma0 = smem_u32(L.epi + ew * 2 * kWarpSlabBytes);
+    const uint32_t bits_s = smem_u32(L.bits + ew * 32 * kBitsWords);
+    float* bias_s = L.bias + half * 3 * kMaxTileN;
+    const uint32_t bias_a = smem_u32(bias_s);
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const float slope = p.slope;
+    const float mneg = p.mask_act == PCADV_ACT_LEAKY ? p.mask_slope : 0.f;
+    const int64_t rpg = p.rows_per_group > 0 ? p.rows_per_group : p.rows;
+    const bool want_bits = p.bits_out != nullptr;
+    uint32_t slab = 0;
+    int staged_col = -1;
+    int64_t staged_g0 = -1, staged_g1 = -1;
+    uint32_t use = 0;
+    // sign-bit words of this thread's row for a whole tile (<= 4 steps x 2 words), fetched one
+    // tile ahead so that their latency hides behind the current tile
+    uint2 mbw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbw[i] = make_uint2(0u, 0u);
+    auto fetch_bits = [&](int64_t tt) {
+      if (tt >= num_tiles) return;
+      const int64_t ttm = tt / tiles_n;
+      const int ttn = static_cast<int>(tt - ttm * tiles_n);
+      const int64_t rr = ttm * kTileM + lane_row;
+      if (rr >= p.rows) return;
+      const uint2* src = reinterpret_cast<const uint2*>(p.mask_bits + rr * p.ld_mask_bits + ((ttn * bn) >> 5));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < steps) mbw[i] = __ldg(src + i);
+    };
+    if (kMaskBits) fetch_bits(blockIdx.x + static_cast<int64_t>(half) * gridDim.x);
+    for (int64_t t = blockIdx.x + static_cast<int64_t>(half) * gridDim.x; t < num_tiles;
+         t += 2 * static_cast<int64_t>(gridDim.x), ++use) {
+      const int64_t tm = t / tiles_n;
+      const int tn = static_cast<int>(t - tm * tiles_n);
+      const int64_t r = tm * kTileM + lane_row;
+      const bool r_ok = r < p.rows;
+      const int col_base = tn * bn;
+      const int32_t row_tma = static_cast<int32_t>(tm * kTileM + quarter * 32);
+      uint32_t gsel = 0;                                  // byte offset of this row's per-cloud bias
+      if (kAdd != kAddNone) {
+        const int64_t row_first = tm * kTileM;
+        const int64_t row_last = row_first + kTileM - 1 < p.rows ? row_first + kTileM - 1 : p.rows - 1;
+        const int64_t g_first = row_first / rpg, g_last = row_last / rpg;
+        const bool restage = col_base != staged_col ||
+                             (kAdd == kAddBiasGroup && (g_first != staged_g0 || g_last != staged_g1));
+        if (restage) {
+          staged_col = col_base; staged_g0 = g_first; staged_g1 = g_last;
+          named_barrier_sync(1 + half, 128);
+          for (int e = hid; e < kMaxTileN; e += 128) {
+            const int c = col_base + e;
+            const bool c_ok = e < bn && c < n;
+            bias_s[e] = (c_ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+            if (kAdd == kAddBiasGroup) {
+              bias_s[kMaxTileN + e] = c_ok ? __ldg(p.group_bias + g_first * n + c) : 0.f;
+              bias_s[2 * kMaxTileN + e] = (c_ok && g_last != g_first) ? __ldg(p.group_bias + g_last * n + c) : 0.f;
+            }
+          }
+          named_barrier_sync(1 + half, 128);
+        }
+        if (kAdd == kAddBiasGroup)
+          gsel = (r_ok && r / rpg != g_first) ? 2u * kMaxTileN * 4u : 1u * kMaxTileN * 4u;
+      }
+      uint2 mbc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mbc[i] = mbw[i];
+      if (kMaskBits) fetch_bits(t + 2 * static_cast<int64_t>(gridDim.x));
+      mbar_wait(&st->tmem_full[half], use & 1);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                              static_cast<uint32_t>(half * kMaxTileN);
+#pragma unroll 1
+      for (int step = 0; step < steps; ++step) {
+        const uint32_t srow = slab0 + slab * kWarpSlabBytes;
+        // the store that last read this slab (two steps ago) is done with it
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+        uint32_t raw[2][32];
+        tmem_ld32_issue(taddr0 + step * 64, raw[0]);
+        tmem_ld32_issue(taddr0 + step * 64 + 32, raw[1]);
+        uint2 mb = mbc[0];
+        if (kMaskBits) {
+          if (step == 1) mb = mbc[1];
+          else if (step == 2) mb = mbc[2];
+          else if (step == 3) mb = mbc[3];
+        }
+        tmem_ld32_wait(raw[0]);
+        tmem_ld32_wait(raw[1]);
+        uint32_t obits[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[h][j]);
+          if (kAdd != kAddNone) {
+            const uint32_t ba = bias_a + static_cast<uint32_t>(step * 64 + h * 32) * 4u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = lds128(ba + q * 16);
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+            if (kAdd == kAddBiasGroup) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b = lds128(ba + gsel + q * 16);
+                v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              }
+            }
+          }
+          if (kAct == PCADV_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (kAct == PCADV_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+          }
+          if (kMaskBits) {
+            const uint32_t word = h == 0 ? mb.x : mb.y;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = (word & (1u << ((j >> 1) + 16 * (j & 1)))) ? v[j] : v[j] * mneg;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            pk[j] = kOut == PCADV_F16 ? pack_f16x2_sat(v[2 * j], v[2 * j + 1]) : pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (want_bits) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w |= pair_gt0_mask<kOut>(pk[j]) & (0x00010001u << j);
+            obits[h] = w;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(srow + (((h * 4 + q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+        if (want_bits) sts64(bits_s + (lane * kBitsWords + 2 * step) * 4, obits[0], obits[1]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d_addr(&maps.out, slab_tma0 + slab * kWarpSlabBytes, col_base + step * 64, row_tma);
+          bulk_commit_group();
+        }
+        slab ^= 1;
+      }
+      if (want_bits) {
+        // the warp's [32 rows][bn / 32 words] sign-bit tile, consecutive lanes on consecutive
+        // 8-byte pairs of a row
+        __syncwarp();
+        const int upr = steps;                             // 8-byte pairs per row in this tile
+        const int64_t wr0 = tm * kTileM + quarter * 32;
+        for (int i = lane; i < 32 * upr; i += 32) {
+          const int rr = i / upr, uu = i - rr * upr;
+          if (wr0 + rr < p.rows) {
+            const uint2 w2 = lds64(bits_s + (rr * kBitsWords + 2 * uu) * 4);
+            *reinterpret_cast<uint2*>(p.bits_out + (wr0 + rr) * p.ld_bits_out + (col_base >> 5) + 2 * uu) = w2;
           }
         }
+        __syncwarp();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&st->tmem_empty[half]);
     }
+    if (lane == 0) bulk_wait_group<0>();
+  }
+  rows_teardown(warp, tmem_base);
+}
+
+typedef void (*RowsKernel)(const TensorMaps, const RowsParams);
+
+template <int kOut>
+static RowsKernel pick_lean(int act, int add, bool maskbits) {
+  if (maskbits) return (act == PCADV_ACT_NONE && add == kAddNone) ? tc_rows_lean_kernel<PCADV_ACT_NONE, kOut, kAddNone, true> : nullptr;
+  if (act == PCADV_ACT_RELU && add == kAddBias) return tc_rows_lean_kernel<PCADV_ACT_RELU, kOut, kAddBias, false>;
+  if (act == PCADV_ACT_RELU && add == kAddBiasGroup) return tc_rows_lean_kernel<PCADV_ACT_RELU, kOut, kAddBiasGroup, false>;
+  if (act == PCADV_ACT_LEAKY && add == kAddBias) return tc_rows_lean_kernel<PCADV_ACT_LEAKY, kOut, kAddBias, false>;
+  return nullptr;
+}
+
+// =====================================================================================
+// kAct: PCADV_ACT_*;  kOut: PCADV_F32 / PCADV_F16 / PCADV_BF16
+template <int kAct, int kOut>
+__global__ void __launch_bounds__(kRowsThreads, 1)
+tc_rows_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const RowsSmem L = carve_rows(smem_raw, p);
+  RowsTail* st = L.tail;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t num_tiles = p.tiles_m * p.tiles_n;
+
+  const uint32_t tmem_base = rows_setup(maps, p, st, warp, lane);
+
+  if (warp == 0) {
+    if (lane == 0) rows_producer(maps, p, L, st, num_tiles);
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      int total_chunks = 0;
-      for (int s = 0; s < p.num_seg; ++s) total_chunks += p.seg_k[s] / kBlockK;
-      int stage = 0;
-      uint32_t phase = 0;
-      int buf = 0;
-      uint32_t buf_phase = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait_backoff(&st->tmem_empty[buf], buf_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kMaxTileN);
-        for (int c = 0; c < total_chunks; ++c) {
-          mbar_wait_backoff(&st->full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(L.stages + stage * p.stage_bytes);
-          mma_chunk_kmajor(d_tmem, a_addr, a_addr + kABytes, p.idesc, c == 0);
-          umma_commit(&st->empty[stage]);
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&st->tmem_full[buf]);
-        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
-      }
-    }
+    if (lane == 0) rows_mma(p, L, st, tmem_base, num_tiles);
   } else {
     // ================= epilogue: two halves x four lane quarters =================
     const int ew = warp - 2;                              // 0..7
@@ -450,15 +726,8 @@ tc_rows_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
     }
     if (lane == 0) bulk_wait_group<0>();                  // all output slabs have landed
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
+  rows_teardown(warp, tmem_base);
 }
-
-typedef void (*RowsKernel)(const TensorMaps, const RowsParams);
 
 template <int kAct>
 static RowsKernel pick_out(int out_dtype) {
@@ -478,8 +747,8 @@ static RowsKernel pick_rows_kernel(int act, int out_dtype) {
 }
 
 static int ensure_rows_smem(const void* kernel) {
-  static const void* done[16] = {nullptr};
-  for (int i = 0; i < 16; ++i) {
+  static const void* done[32] = {nullptr};
+  for (int i = 0; i < 32; ++i) {
     if (done[i] == kernel) return 0;
     if (done[i] == nullptr) {
       PCADV_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -530,13 +799,36 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
     if (int rc = encode_tmap_2d(&maps.out, a.out, out_dt, a.rows, a.n, a.ld_out, 128 / esz, 32))
       return rc;
   }
-  p.tma_mask = (p.tma_out && a.mask && a.mask_act != PCADV_ACT_NONE && out_dt != PCADV_F32 &&
+  if (a.bits_out || a.mask_bits) {
+    PCADV_CHECK_ARG(a.n % 64 == 0, "tc_linear: bit masks need n %% 64 == 0 (n=%d)", a.n);
+    PCADV_CHECK_ARG(!a.bits_out || (a.out && out_dt != PCADV_F32 && a.ld_bits_out % 2 == 0 &&
+                                    (reinterpret_cast<uintptr_t>(a.bits_out) & 7) == 0),
+                    "tc_linear: bits_out needs a 16-bit output and 8-byte aligned rows");
+    PCADV_CHECK_ARG(!a.mask_bits || out_dt != PCADV_F32, "tc_linear: mask_bits needs a 16-bit output");
+    PCADV_CHECK_ARG(!a.mask_bits || (a.ld_mask_bits % 2 == 0 && (reinterpret_cast<uintptr_t>(a.mask_bits) & 7) == 0),
+                    "tc_linear: mask_bits rows must be 8-byte aligned");
+  }
+  p.bits_out = a.bits_out; p.ld_bits_out = a.ld_bits_out;
+  p.mask_bits = a.mask_act != PCADV_ACT_NONE ? a.mask_bits : nullptr; p.ld_mask_bits = a.ld_mask_bits;
+  // ---- the lean kernel takes the common shapes; everything else goes to the general one
+  RowsKernel lean = nullptr;
+  if (p.tma_out && out_dt != PCADV_F32 && a.n % 64 == 0 && !a.addend && !a.rowmax_key && !a.out_scale &&
+      (!a.mask || a.mask_act == PCADV_ACT_NONE || p.mask_bits) &&
+      (!a.group_bias || a.rows_per_group >= kTileM)) {
+    const int add = a.group_bias ? kAddBiasGroup : (a.bias ? kAddBias : kAddNone);
+    lean = out_dt == PCADV_F16 ? pick_lean<PCADV_F16>(a.act, add, p.mask_bits != nullptr)
+                               : pick_lean<PCADV_BF16>(a.act, add, p.mask_bits != nullptr);
+  }
+  PCADV_CHECK_ARG(lean || (!a.bits_out && !p.mask_bits),
+                  "tc_linear: bit masks are only implemented for the lean layer shapes");
+  p.tma_mask = (!lean && p.tma_out && a.mask && a.mask_act != PCADV_ACT_NONE && out_dt != PCADV_F32 &&
                 a.mask_dtype != PCADV_F32 && tma_compatible(a.mask, a.mask_dtype, a.ld_mask)) ? 1 : 0;
   if (p.tma_mask) {
     if (int rc = encode_tmap_2d(&maps.mask, a.mask, a.mask_dtype, a.rows, a.n, a.ld_mask, 64, 32))
       return rc;
   }
   p.nslabs = p.tma_mask ? 3 : 2;
+  if (lean) { p.tma_mask = 0; p.nslabs = 2; }
   // row-compact staging when rows are not TMA-storable but contiguous (fc4: 50 fp32 logits)
   p.compact_out = (a.out && !p.tma_out && a.ld_out == a.n && p.tiles_n == 1 &&
                    (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.n * esz) % 4 == 0 &&
@@ -549,7 +841,7 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
   PCADV_CHECK_ARG(smem <= static_cast<size_t>(kRowsSmemMax), "tc_linear: shared memory budget exceeded");
   const int64_t tiles = p.tiles_m * p.tiles_n;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  RowsKernel k = pick_rows_kernel(a.act, out_dt);
+  RowsKernel k = lean ? lean : pick_rows_kernel(a.act, out_dt);
   if (int rc = ensure_rows_smem(reinterpret_cast<const void*>(k))) return rc;
   k<<<grid, kRowsThreads, smem, s>>>(maps, p);
   PCADV_LAUNCHED();

@@ -35,19 +35,29 @@ def compute_weight(prec, w32, k_list, n):
     return w32
 
 
-def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, group_bias=None):
+def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, group_bias=None,
+                  bits=None):
     """Run ``layers`` on the K-concat of ``x_segs``.  ``group_bias`` (per-cloud
-    bias) applies to the first layer.  Returns the list of layer outputs."""
+    bias) applies to the first layer.  Returns the list of layer outputs.  ``bits``: a list that
+    receives, per layer, the 1-bit map [y > 0] of an activated output (or None where the layer
+    cannot emit it) -- what the backward reads instead of the 16-bit activation."""
     ys = []
     segs = list(x_segs)
     for i, L in enumerate(layers):
         last = i == len(layers) - 1
-        w = compute_weight(prec, L.w, [s.shape[1] for s in segs], L.w.shape[0])
+        n = L.w.shape[0]
+        w = compute_weight(prec, L.w, [s.shape[1] for s in segs], n)
         out_dtype = torch.float32 if (last and final_fp32) else prec.act_dtype
+        b = None
+        if bits is not None and L.act != ACT_NONE and out_dtype != torch.float32 and \
+                ops.bits_eligible(prec, segs, w, n):
+            b = ops.new_bits(segs[0].shape[0], n, segs[0].device)
         y, _, _ = ops.linear(segs, w, bias=L.b, act=L.act, slope=L.slope, out_dtype=out_dtype,
                              engine=prec.engine, rows_per_group=rows_per_group if i == 0 else 0,
-                             group_bias=group_bias if i == 0 else None)
+                             group_bias=group_bias if i == 0 else None, bits_out=b)
         ys.append(y)
+        if bits is not None:
+            bits.append(b)
         segs = [y]
     return ys
 
@@ -111,7 +121,7 @@ def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0)
 
 
 def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, scale2, addends=None,
-                   dx_packed=False):
+                   dx_packed=False, bits=None):
     """Backward through a chain.  ``dz_last``: dz of the last layer ([rows, pad(n)]).
     ``need_w[i]`` / ``need_b[i]``: which parameter gradients to form (frozen
     discriminators skip wgrad, utils/trainer.py:885-886).  Returns
@@ -132,7 +142,8 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
         wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz.shape[1]])
         dz, _, _ = ops.linear([dz], wt, mask=ys[i - 1], mask_act=P.act, mask_slope=P.slope,
                               out_dtype=prec.act_dtype, engine=prec.engine,
-                              addend=addends.get(i - 1))
+                              addend=addends.get(i - 1),
+                              mask_bits=bits[i - 1] if bits is not None else None)
     dx = None
     if need_x:
         L = layers[0]

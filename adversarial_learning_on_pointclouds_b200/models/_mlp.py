@@ -79,9 +79,10 @@ class PointMLPFunction(torch.autograd.Function):
         body = layers if spec.reduce is None else layers[:-1]
         if gb is not None:
             gb = gb.contiguous().float()
+        ybits = []
         ys = chain_forward(prec, [x_in], body, final_fp32=(spec.reduce is None),
                            rows_per_group=spec.group if gb is not None else 0,
-                           group_bias=gb) if body else []
+                           group_bias=gb, bits=ybits) if body else []
         red_val = red_idx = None
         if spec.reduce is not None:
             L = layers[-1]
@@ -100,7 +101,9 @@ class PointMLPFunction(torch.autograd.Function):
         ctx.n_ys = len(ys)
         ctx.has_red = red_val is not None
         ctx.has_gb = gb is not None
-        saved = [x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) + list(params)
+        ctx.bit_slots = [i for i, t in enumerate(ybits) if t is not None]
+        saved = [x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) + list(params) + \
+            [ybits[i] for i in ctx.bit_slots]
         ctx.save_for_backward(*saved)
         if tap is not None:
             return out, tap
@@ -110,6 +113,11 @@ class PointMLPFunction(torch.autograd.Function):
     def backward(ctx, d_out, d_tap=None):
         prec, spec = ctx.prec, ctx.spec
         sv = list(ctx.saved_tensors)
+        nb = len(ctx.bit_slots)
+        ybits = [None] * ctx.n_ys
+        for slot, t in zip(ctx.bit_slots, sv[len(sv) - nb:]):
+            ybits[slot] = t
+        sv = sv[:len(sv) - nb]
         x_in, ys = sv[0], sv[1:1 + ctx.n_ys]
         pos = 1 + ctx.n_ys
         red_val = red_idx = None
@@ -213,13 +221,13 @@ class PointMLPFunction(torch.autograd.Function):
                                mask_slope=P_.slope)
             g2, dx, dz0 = chain_backward(prec, dz_t, [x_in], ys[:t + 1], body[:t + 1],
                                          need_w[:t + 1], need_b[:t + 1], need_x, scale2,
-                                         dx_packed=ctx.packed_in)
+                                         dx_packed=ctx.packed_in, bits=ybits[:t + 1])
             for i, gr in enumerate(g2):
                 grads[i] = gr
         elif body and dz_last is not None:
             g2, dx, dz0 = chain_backward(prec, dz_last, [x_in], ys[:len(body)], body,
                                          need_w[:len(body)], need_b[:len(body)], need_x, scale2,
-                                         addends=addends, dx_packed=ctx.packed_in)
+                                         addends=addends, dx_packed=ctx.packed_in, bits=ybits[:len(body)])
             for i, gr in enumerate(g2):
                 grads[i] = gr
         dgb = None

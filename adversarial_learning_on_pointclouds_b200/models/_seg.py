@@ -67,7 +67,8 @@ class SegFunction(torch.autograd.Function):
         b = {n: p[n + ".bias"] for n in _TRUNK + _HEAD}
 
         # trunk: conv1 (K=3, CUDA-core, HBM-bound) then conv2..conv5
-        xs = chain_forward(prec, [pts2], [Layer(W[n], b[n], ACT_RELU) for n in _TRUNK[:5]])
+        xbits, hbits = [], []
+        xs = chain_forward(prec, [pts2], [Layer(W[n], b[n], ACT_RELU) for n in _TRUNK[:5]], bits=xbits)
         x5 = xs[4]
         # conv6 + ReLU + max over the cloud, fused; the B x 2048 x N map is never stored
         w6 = compute_weight(prec, W["conv6"], [512], 2048)
@@ -80,7 +81,7 @@ class SegFunction(torch.autograd.Function):
                                       Layer(W["fc2"], b["fc2"], ACT_RELU),
                                       Layer(W["fc3"], b["fc3"], ACT_RELU),
                                       Layer(W["fc4"], b["fc4"], ACT_NONE)],
-                           final_fp32=True, rows_per_group=N, group_bias=cbias)
+                           final_fp32=True, rows_per_group=N, group_bias=cbias, bits=hbits)
         logits = hs[3].view(B, N, -1)
         k_out = logits.shape[2]
         cols = pad64(k_out) if prec.scaled else k_out
@@ -103,7 +104,12 @@ class SegFunction(torch.autograd.Function):
         else:
             raise ValueError("head must be 'logits', 'ce' or 'lsm'")
         ctx.has_keep = keep is not None
-        ctx.save_for_backward(pts2, cls2, g, idx, *xs, *hs[:3], *params, *([keep] if keep is not None else []))
+        # 1-bit activation masks [x > 0] of x1..x5 / h1..h3 where the layer could emit them
+        bit_list = xbits + hbits[:3]
+        ctx.bit_slots = [i for i, t in enumerate(bit_list) if t is not None]
+        ctx.save_for_backward(pts2, cls2, g, idx, *xs, *hs[:3], *params,
+                              *([keep] if keep is not None else []),
+                              *[bit_list[i] for i in ctx.bit_slots])
         if debug is not None:
             debug.update(x=xs, h=hs[:3], g=g, idx=idx, cbias=cbias, logits=logits)
         if head == "ce":
@@ -157,6 +163,12 @@ class SegFunction(torch.autograd.Function):
         sv = ctx.saved_tensors
         pts2, cls2, g, idx = sv[0:4]
         xs, hs = list(sv[4:9]), list(sv[9:12])
+        nb = len(ctx.bit_slots)
+        bit_list = [None] * 8
+        for slot, t in zip(ctx.bit_slots, sv[len(sv) - nb:]):
+            bit_list[slot] = t
+        xbits, hbits = bit_list[:5], bit_list[5:]
+        sv = sv[:len(sv) - nb]
         keep = sv[-1] if ctx.has_keep else None
         params = sv[12:-1] if ctx.has_keep else sv[12:]
         p = dict(zip(PARAM_NAMES, params))
@@ -203,7 +215,7 @@ class SegFunction(torch.autograd.Function):
             grads[name + ".weight"], grads[name + ".bias"] = dw, db
             wt = dgrad_weight(prec, [W[name]], W[name].shape[1], [dz.shape[1]])
             dz, _, _ = ops.linear([dz], wt, mask=xin, mask_act=ACT_RELU, out_dtype=prec.act_dtype,
-                                  engine=prec.engine)
+                                  engine=prec.engine, mask_bits=hbits[2 - li])
         dz_fc1 = dz                                                   # [P, 256], scaled
 
         # ---- fc1: per-point part (x1..x5) and per-cloud part (g, cls, bias) -----------
@@ -232,7 +244,7 @@ class SegFunction(torch.autograd.Function):
         if ops.maxpool_inplace_eligible(512, N, 2048):
             # dense part first; the max-pool's sparse part (argmax rows only) is added in place
             dz, _, _ = ops.linear([dz_fc1], wt, mask=xs[4], mask_act=ACT_RELU,
-                                  out_dtype=prec.act_dtype, engine=prec.engine)
+                                  out_dtype=prec.act_dtype, engine=prec.engine, mask_bits=xbits[4])
             ops.maxpool_bwd(dg, g, idx, xs[4], w6, N, act=ACT_RELU, dw=dw6, dbias=db6,
                             dz_inout=dz, prev_act=ACT_RELU, scale=inv)
         else:
@@ -253,7 +265,7 @@ class SegFunction(torch.autograd.Function):
             wt = dgrad_weight(prec, [W[name], W["fc1"][:, sl[0]:sl[1]]], W[name].shape[1],
                               [dz.shape[1], 256])
             dz, _, _ = ops.linear([dz, dz_fc1], wt, mask=xin, mask_act=ACT_RELU,
-                                  out_dtype=prec.act_dtype, engine=prec.engine)
+                                  out_dtype=prec.act_dtype, engine=prec.engine, mask_bits=xbits[li - 1])
         dw, db = layer_wgrad(prec, dz, [pts2], W["conv1"].shape, need["conv1.weight"],
                              need["conv1.bias"], scale2)
         grads["conv1.weight"], grads["conv1.bias"] = dw, db

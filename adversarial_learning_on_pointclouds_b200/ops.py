@@ -132,9 +132,12 @@ def tc_eligible(segs, w, n):
 
 def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None, act=ACT_NONE,
            slope=0.0, mask=None, mask_act=ACT_NONE, mask_slope=0.0, out_dtype=torch.float32,
-           out_scale=None, want_out=True, colmax=False, rowmax=False, engine=ENGINE_SIMT, n=None):
+           out_scale=None, want_out=True, colmax=False, rowmax=False, engine=ENGINE_SIMT, n=None,
+           bits_out=None, mask_bits=None):
     """See ``pcadv_linear`` in include/pcadv.h.  Returns (out | None, colmax_key |
-    None, rowmax_key | None)."""
+    None, rowmax_key | None).  ``bits_out``: a ``new_bits(rows, n)`` tensor that receives the
+    sign bits of the output; ``mask_bits``: such a tensor used instead of ``mask`` (both only
+    where ``bits_eligible`` holds)."""
     a = _lib.LinearArgs()
     rows = segs[0].shape[0]
     n = int(n if n is not None else w.shape[0])
@@ -165,10 +168,22 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
             raise ValueError("addend must be fp32")
         a.addend, a.ld_addend = p, ld
     a.act, a.slope = act, float(slope)
-    if mask is not None:
+    use_bits = mask_bits is not None and engine == ENGINE_TC and out_dtype != torch.float32 and \
+        addend is None and out_scale is None and not rowmax and n % 64 == 0 and act == ACT_NONE and \
+        bias is None and group_bias is None
+    if use_bits:
+        a.mask_bits, a.ld_mask_bits = C.c_void_p(mask_bits.data_ptr()), mask_bits.stride(0)
+        a.mask_act, a.mask_slope = mask_act, float(mask_slope)
+    elif mask is not None:
         p, ld, dt = _mat(mask)
         a.mask, a.ld_mask, a.mask_dtype = p, ld, dt
         a.mask_act, a.mask_slope = mask_act, float(mask_slope)
+    elif mask_bits is not None:
+        raise ValueError("mask_bits needs the tensor-core engine and a 16-bit output (pass mask too)")
+    if bits_out is not None:
+        if engine != ENGINE_TC or out_dtype == torch.float32 or not want_out:
+            raise ValueError("bits_out needs the tensor-core engine and a 16-bit output")
+        a.bits_out, a.ld_bits_out = C.c_void_p(bits_out.data_ptr()), bits_out.stride(0)
     a.out_scale = _f32(out_scale) if out_scale is not None else None
     out = ckey = rkey = None
     a.out_dtype = _DT[out_dtype]
@@ -185,10 +200,23 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
         a.rowmax_key = C.c_void_p(rkey.data_ptr())
     tag = "linear:%s:k%d:n%d%s%s%s%s" % ("tc" if engine == ENGINE_TC else "simt", ktot, n,
                                        ":colmax" if colmax else "", ":rowmax" if rowmax else "",
-                                       ":mask" if mask is not None else "",
+                                       ":maskbits" if use_bits else (":mask" if mask is not None else ""),
                                        ":addend" if addend is not None else "")
     _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream())
     return out, ckey, rkey
+
+
+def bits_eligible(prec, segs, w, n):
+    """True when a layer can emit / consume the 1-bit activation mask: tensor-core engine,
+    16-bit storage, n a multiple of 64."""
+    return prec.engine == ENGINE_TC and prec.act_dtype != torch.float32 and n % 64 == 0 and \
+        tc_eligible(segs, w, n)
+
+
+def new_bits(rows, n, device):
+    """Sign-bit map of a [rows, n] activation: uint32 words, column c in word c // 32 (bit layout
+    in include/pcadv.h)."""
+    return torch.empty((rows, n // 32), dtype=torch.int32, device=device)
 
 
 def wgrad(dz, segs, *, dw=None, dbias=None, dgroup_bias=None, rows_per_group=0, scale=None,

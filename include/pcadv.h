@@ -55,7 +55,7 @@ typedef struct pcadv_seg {
  * pcadv_linear: out[r, c] = post( sum_seg sum_k seg[r, k] * w[c, koff_seg + k]
  *                                  + bias[c] + group_bias[r / rows_per_group, c]
  *                                  + addend[r, c] )
- *   post(v) = act(v) * act'(mask[r, c]) * (*out_scale)
+ *   post(v) = act(v) * act'(mask[r, c]) * (*out_scale)      (mask, or its 1-bit form mask_bits)
  * Replaces: Conv1d(k=1) + F.relu        models/pointnet.py:115-128, :291-301
  *           nn.Linear on B x N x C      models/pointnet.py:309-314
  *           the discriminator convs     models/discriminator.py:22-24, :44-48, :64-67
@@ -97,6 +97,15 @@ typedef struct pcadv_linear_args {
   int64_t ld_out;
   unsigned long long* colmax_key;
   unsigned long long* rowmax_key;
+  /* Sign bits of the activation, so that the backward reads 1 bit instead of 16 per element
+   * (tensor-core engine, 16-bit TMA-storable out, n a multiple of 64, no addend / rowmax / out_scale):
+   *   bits_out[r, c / 32], bit ((c % 32) / 2 + 16 * (c % 2)) = [stored out[r, c] > 0]   (written with out)
+   *   mask_bits: the same map of the forward layer, used INSTEAD of mask: act'(.) = bit ? 1 : mask_slope
+   * Row-major uint32 words with leading dimensions ld_bits_out / ld_mask_bits (words, even). */
+  uint32_t* bits_out;
+  int64_t ld_bits_out;
+  const uint32_t* mask_bits;
+  int64_t ld_mask_bits;
 } pcadv_linear_args;
 
 int pcadv_linear(const pcadv_linear_args* a, void* stream);

@@ -91,3 +91,31 @@ def test_tc_wgrad(dtype, rows, ks, n):
     e1, e2 = rel_err(dw, 0.5 * dz.double().t() @ x), rel_err(db, 0.5 * dz.double().sum(0))
     print(dtype, rows, ks, n, "dw", e1, "db", e2)
     assert e1 < 1e-5 and e2 < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,k,n,act", [(1000, 64, 64, ACT_RELU), (4133, 128, 512, ACT_RELU),
+                                          (2500, 256, 256, ACT_LEAKY), (129, 64, 128, ACT_RELU)])
+def test_tc_bit_masks(dtype, rows, k, n, act):
+    """bits_out is exactly [stored output > 0]; a dgrad that reads mask_bits equals the one that
+    reads the 16-bit mask."""
+    x = _rand((rows, k), 21, dtype)
+    w = _rand((n, k), 22, dtype, 0.1)
+    bias = _rand((n,), 23, torch.float32)
+    bits = ops.new_bits(rows, n, DEV)
+    bits.fill_(-1)
+    y, _, _ = ops.linear([x], w, bias=bias, act=act, slope=0.2, out_dtype=dtype, engine=ENGINE_TC,
+                         bits_out=bits)
+    # word w covers columns 32 w .. 32 w + 31: column 2 k at bit k, column 2 k + 1 at bit 16 + k
+    j = torch.arange(32, device=DEV, dtype=torch.int64)
+    shifts = (j >> 1) + 16 * (j & 1)
+    got = ((bits.long().unsqueeze(2) >> shifts) & 1).reshape(rows, n).bool()
+    assert torch.equal(got, y.float() > 0)
+    dz = _rand((rows, n), 24, dtype)
+    wt = _rand((k if k % 64 == 0 else 64, n), 25, dtype, 0.1)
+    # dgrad of a following layer: output width n' = wt rows must match the mask width -> use n x n
+    w2 = _rand((n, n), 26, dtype, 0.1)
+    a, _, _ = ops.linear([dz], w2, mask=y, mask_act=act, mask_slope=0.2, out_dtype=dtype, engine=ENGINE_TC)
+    b, _, _ = ops.linear([dz], w2, mask=y, mask_act=act, mask_slope=0.2, out_dtype=dtype, engine=ENGINE_TC,
+                         mask_bits=bits)
+    assert torch.equal(a, b)

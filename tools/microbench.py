@@ -28,7 +28,7 @@ def cases(P, N):
     c = {}
 
     def lin(name, ks, n, out_dtype=torch.float16, mask=False, addend=False, bias=True, colmax=False,
-            rowmax=False, want_out=True, gb=False):
+            rowmax=False, want_out=True, gb=False, bits=False, maskbits=False):
         segs = [r16((P, k)) for k in ks]
         w = r16((n, sum(ks)), 0.05)
         kw = dict(bias=torch.randn(n, device=DEV) if bias else None, act=ACT_RELU, out_dtype=out_dtype,
@@ -40,6 +40,11 @@ def cases(P, N):
             kw.update(addend=torch.randn((P, n), device=DEV))
         if gb:
             kw.update(group_bias=torch.randn((B, n), device=DEV))
+        if bits:
+            kw.update(bits_out=ops.new_bits(P, n, DEV))
+        if maskbits:
+            kw.update(mask=r16((P, n)), mask_act=ACT_RELU,
+                      mask_bits=torch.randint(-2 ** 31, 2 ** 31 - 1, (P, n // 32), device=DEV, dtype=torch.int32))
         esz = 2 if out_dtype == torch.float16 else 4
         nbytes = P * (2 * sum(ks) + (esz * n if want_out else 0) + (2 * n if mask else 0) +
                       (4 * n if addend else 0))
@@ -49,6 +54,11 @@ def cases(P, N):
     lin("conv2", [64], 128)
     lin("conv3", [128], 128)
     lin("conv5", [128], 512)
+    lin("conv5_bits", [128], 512, bits=True)
+    lin("conv3_bits", [128], 128, bits=True)
+    lin("fc2_bits", [256], 256, bits=True)
+    lin("dz_fc1_mb", [256], 256, maskbits=True, bias=False)
+    lin("dz4_mb", [512, 256], 128, maskbits=True, bias=False)
     lin("conv6max", [512], 2048, colmax=True, want_out=False)
     lin("fc1", [64, 128, 128, 128, 512], 256, gb=True, bias=False)
     lin("fc2", [256], 256)
