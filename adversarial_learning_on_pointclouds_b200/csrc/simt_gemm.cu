@@ -444,6 +444,69 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const pcadv_wgra
   }
 }
 
+// =====================================================================================
+// Thin GEMM for the per-cloud layers (rows = clouds, a few hundred at most; K up to a few
+// thousand): the fold of the tiled global feature into a per-cloud bias (models/pointnet.py
+// :304-309), the T-Net / classifier heads.  One CTA = an 8 x 8 output tile with the whole K
+// range split over its 256 threads (consecutive lanes on consecutive k: coalesced operand
+// reads), then a shuffle + shared-memory reduction -- enough CTAs to fill the GPU where the
+// 128 x 64 tiling of simt_linear_kernel would launch a handful.
+// =====================================================================================
+constexpr int TR = 8, TC = 8;
+
+__global__ void __launch_bounds__(256) thin_linear_kernel(const pcadv_linear_args a) {
+  __shared__ float red[8][TR * TC];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * TR;
+  const int col0 = blockIdx.y * TC;
+  float acc[TR][TC];
+#pragma unroll
+  for (int i = 0; i < TR; ++i)
+#pragma unroll
+    for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
+  int koff = 0;
+  for (int s = 0; s < a.num_seg; ++s) {
+    const pcadv_seg sg = a.seg[s];
+    for (int k = t; k < sg.k; k += 256) {
+      float av[TR], wv[TC];
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+        av[i] = row0 + i < a.rows ? ld_as_float(sg.ptr, (row0 + i) * sg.ld + k, sg.dtype) : 0.f;
+#pragma unroll
+      for (int j = 0; j < TC; ++j)
+        wv[j] = col0 + j < a.n ? ld_as_float(a.w, static_cast<int64_t>(col0 + j) * a.ldw + koff + k, a.w_dtype) : 0.f;
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    koff += sg.k;
+  }
+#pragma unroll
+  for (int i = 0; i < TR; ++i)
+#pragma unroll
+    for (int j = 0; j < TC; ++j) {
+      float v = acc[i][j];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][i * TC + j] = v;
+    }
+  __syncthreads();
+  if (t < TR * TC) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][t];
+    const int64_t r = row0 + t / TC;
+    const int c = col0 + t % TC;
+    if (r < a.rows && c < a.n) {
+      if (a.bias) v += a.bias[c];
+      v = apply_act(v, a.act, a.slope);
+      if (a.out_scale) v *= *a.out_scale;
+      st_from_float(a.out, r * a.ld_out + c, a.out_dtype, v);
+    }
+  }
+}
+
 }  // namespace
 
 static bool first_layer_wgrad_eligible(const pcadv_wgrad_args& a) {
@@ -474,6 +537,15 @@ int simt_linear(const pcadv_linear_args& a, cudaStream_t s) {
       case 3: first_layer_kernel<3><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a); break;
       default: first_layer_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a); break;
     }
+    PCADV_LAUNCHED();
+    return 0;
+  }
+  int ktot = 0;
+  for (int i = 0; i < a.num_seg; ++i) ktot += a.seg[i].k;
+  if (a.rows <= 1024 && ktot >= 256 && a.out && !a.group_bias && !a.addend && !a.mask && !a.colmax_key &&
+      !a.rowmax_key) {
+    dim3 grid(static_cast<unsigned>((a.rows + TR - 1) / TR), (a.n + TC - 1) / TC);
+    thin_linear_kernel<<<grid, 256, 0, s>>>(a);
     PCADV_LAUNCHED();
     return 0;
   }

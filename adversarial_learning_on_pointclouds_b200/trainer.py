@@ -186,6 +186,35 @@ class GraphedAdversarialSegStep:
             self.losses = torch.stack(run())
         self.launches_per_step = _lib.launch_count() - before
 
+    # ---- input pipeline: the next batch's host -> device copy runs on a
+    # copy stream under the current step; the step then moves it into the graph's static buffers
+    # with a device-to-device copy
+    def prefetch(self, batch_gt, batch_nogt):
+        """Start copying the NEXT step's (pinned) host batch to device staging buffers."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_gt = tuple(torch.empty_like(t) for t in self.static_gt)
+            self._stage_nogt = tuple(torch.empty_like(t) for t in self.static_nogt)
+            self._staged = torch.cuda.Event()
+            self._consumed = None
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)                  # staging was read by the previous step
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage_gt + self._stage_nogt, tuple(batch_gt) + tuple(batch_nogt)):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record(cs)
+
+    def step_prefetched(self):
+        """Run one step on the batch handed to the last ``prefetch`` call."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for dst, src in zip(self.static_gt + self.static_nogt, self._stage_gt + self._stage_nogt):
+            dst.copy_(src, non_blocking=True)
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(cur)
+        return self()
+
     def _draw_labels(self, slot):
         """Same draws, same order as make_D_label(random=True) at utils/trainer.py:940-945 and
         :955-960 (CPU generator), into pinned host slot ``slot``."""
