@@ -346,9 +346,16 @@ def run_cuda(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample(args, N)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() can block for minutes when a
+        # captured CUDA graph still holds the communicator's kernels (seen on 2 x B200), and
+        # nothing is left to flush.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def tot_points_per_launch(ksum, Bg, Bn, N):
