@@ -61,7 +61,6 @@ extern "C" int pcadv_linear(const pcadv_linear_args* a, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->engine == PCADV_ENGINE_TC) return tc_linear(*a, s);
   PCADV_CHECK_ARG(a->engine == PCADV_ENGINE_SIMT, "pcadv_linear: unknown engine %d", a->engine);
-  PCADV_CHECK_ARG(!a->bits_out && !a->mask_bits, "pcadv_linear: bit masks need the tensor-core engine");
   return simt_linear(*a, s);
 }
 

@@ -15,6 +15,14 @@ namespace {
 
 constexpr int kHeadMaxN = 128;     // classes per row the kernels accept
 
+// 16-bit point-major [rows, 64] outputs leave through a per-warp [32 rows][128 B] staging tile and
+// fully coalesced 16-byte stores (a warp's 32 rows are 4 KB contiguous in HBM).
+constexpr int kPitchW = 33;        // staging row pitch in 32-bit words: conflict-free rows and columns
+__device__ __forceinline__ void flush_tile16(const uint32_t* stage, void* dst, int64_t row0, int nrows, int lane) {
+  uint32_t* g = reinterpret_cast<uint32_t*>(dst) + row0 * 32;
+  for (int r = 0; r < nrows; ++r) g[r * 32 + lane] = stage[r * kPitchW + lane];
+}
+
 // A warp owns 32 consecutive rows: the [32, n] fp32 logits tile is fetched coalesced into
 // shared memory (odd row stride: conflict-free row-per-thread reads); then thread = row.
 __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args a) {
@@ -23,7 +31,13 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
   const int ldt = n | 1;                                   // odd stride
-  float* tile = sm + static_cast<size_t>(warp) * 32 * ldt;
+  float* tile = sm + static_cast<size_t>(warp) * (32 * ldt + 32 * kPitchW);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(tile + 32 * ldt);     // [32 rows][33 words]
+  // packed fast path: 16-bit outputs of exactly 64 columns with contiguous rows
+  const bool packed_p = a.probs && a.probs_dtype != PCADV_F32 && a.probs_cols == 64 && a.ld_probs == 64 &&
+                        (reinterpret_cast<uintptr_t>(a.probs) & 15) == 0 && n <= 64;
+  const bool packed_d = a.dz && a.dz_dtype != PCADV_F32 && a.dz_cols == 64 && a.ld_dz == 64 &&
+                        (reinterpret_cast<uintptr_t>(a.dz) & 15) == 0 && n <= 64;
   const int64_t nblk = (a.rows + 31) / 32;
   float loss = 0.f;
   for (int64_t blk = static_cast<int64_t>(blockIdx.x) * 8 + warp; blk < nblk;
@@ -43,40 +57,65 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
         for (int c = lane; c < n; c += 32) tile[r * ldt + c] = __ldg(a.logits + (row0 + r) * a.ld + c);
     }
     __syncwarp();
+    float lse = 0.f;
+    int label = -1;
+    float* t = tile + lane * ldt;
+    const int64_t row = row0 + lane;
     if (lane < nrows) {
-      float* t = tile + lane * ldt;
-      const int64_t row = row0 + lane;
       float m = t[0];
       for (int c = 1; c < n; ++c) m = fmaxf(m, t[c]);
       float s = 0.f;
-      for (int c = 0; c < n; ++c) s += expf(t[c] - m);
-      const float lse = m + logf(s);
-      int label = -1;
+      for (int c = 0; c < n; ++c) s += __expf(t[c] - m);
+      lse = m + __logf(s);
       if (a.labels) {
         label = static_cast<int>(a.labels[row]);
         if (label >= 0 && label < n) loss += lse - t[label];
       }
-      // outputs, 8 columns at a time (vector stores when the row address allows)
-      const int cols_p = a.probs ? a.probs_cols : 0;
-      const int cols_d = a.dz ? a.dz_cols : 0;
-      const int cmax = cols_p > cols_d ? cols_p : cols_d;
-      for (int c0 = 0; c0 < cmax; c0 += 8) {
-        float p[8], d[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = c0 + j;
-          const float lp = c < n ? t[c] - lse : 0.f;
-          const float pr = c < n ? expf(lp) : 0.f;
-          p[j] = a.mode == PCADV_HEAD_LSM ? lp : pr;
-          d[j] = c < n ? a.dz_gain * (pr - (c == label ? 1.f : 0.f)) : 0.f;
+      // in place: t[c] <- log_softmax
+      for (int c = 0; c < n; ++c) t[c] -= lse;
+    }
+    // ---- probs (softmax, or log_softmax in LSM mode)
+    if (a.probs) {
+      if (packed_p) {
+        if (lane < nrows) {
+          uint32_t* srow = stage + lane * kPitchW;
+#pragma unroll 4
+          for (int c = 0; c < 64; c += 2) {
+            float v0 = c < n ? t[c] : 0.f, v1 = c + 1 < n ? t[c + 1] : 0.f;
+            if (a.mode == PCADV_HEAD_CE) { v0 = c < n ? __expf(v0) : 0.f; v1 = c + 1 < n ? __expf(v1) : 0.f; }
+            srow[c >> 1] = a.probs_dtype == PCADV_F16 ? pack_f16x2_sat(v0, v1) : pack_bf16x2(v0, v1);
+          }
         }
-        if (c0 < cols_p) {
-          if (c0 + 8 <= cols_p) store8(a.probs, row * a.ld_probs + c0, a.probs_dtype, p);
-          else for (int j = 0; c0 + j < cols_p; ++j) st_from_float(a.probs, row * a.ld_probs + c0 + j, a.probs_dtype, p[j]);
+        __syncwarp();
+        flush_tile16(stage, a.probs, row0, nrows, lane);
+        __syncwarp();
+      } else if (lane < nrows) {
+        for (int c = 0; c < a.probs_cols; ++c) {
+          float v = c < n ? t[c] : 0.f;
+          if (a.mode == PCADV_HEAD_CE && c < n) v = __expf(v);
+          st_from_float(a.probs, row * a.ld_probs + c, a.probs_dtype, v);
         }
-        if (c0 < cols_d) {
-          if (c0 + 8 <= cols_d) store8(a.dz, row * a.ld_dz + c0, a.dz_dtype, d);
-          else for (int j = 0; c0 + j < cols_d; ++j) st_from_float(a.dz, row * a.ld_dz + c0 + j, a.dz_dtype, d[j]);
+      }
+    }
+    // ---- dz = gain * (softmax - onehot)
+    if (a.dz) {
+      if (packed_d) {
+        if (lane < nrows) {
+          uint32_t* srow = stage + lane * kPitchW;
+#pragma unroll 4
+          for (int c = 0; c < 64; c += 2) {
+            const float v0 = c < n ? a.dz_gain * (__expf(t[c]) - (c == label ? 1.f : 0.f)) : 0.f;
+            const float v1 = c + 1 < n ? a.dz_gain * (__expf(t[c + 1]) - (c + 1 == label ? 1.f : 0.f)) : 0.f;
+            srow[c >> 1] = a.dz_dtype == PCADV_F16 ? pack_f16x2_sat(v0, v1) : pack_bf16x2(v0, v1);
+          }
+        }
+        __syncwarp();
+        flush_tile16(stage, a.dz, row0, nrows, lane);
+        __syncwarp();
+      } else if (lane < nrows) {
+        for (int c = 0; c < a.dz_cols; ++c) {
+          const float v = c < n ? a.dz_gain * (__expf(t[c]) - (c == label ? 1.f : 0.f)) : 0.f;
+          st_from_float(a.dz, row * a.ld_dz + c, a.dz_dtype, v);
         }
       }
     }
@@ -91,6 +130,57 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
       for (int w = 0; w < 8; ++w) s += red[w];
       atomicAdd(a.loss_sum, s);
     }
+  }
+}
+
+// Packed path ([rows, 64] 16-bit lp / dy / dz with contiguous rows): a warp stages its 32 rows of
+// lp and dy with coalesced 16-byte loads, thread = row computes in place, coalesced store.
+__global__ void __launch_bounds__(128) logsoftmax_bwd16_kernel(const uint32_t* __restrict__ lp,
+                                                              const uint32_t* __restrict__ dy, int64_t rows,
+                                                              int n, const float* scale, uint32_t* dz, int bf16) {
+  __shared__ uint32_t sm_lp[4][32 * kPitchW];
+  __shared__ uint32_t sm_dy[4][32 * kPitchW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float sc = scale ? *scale : 1.f;
+  const int64_t nblk = (rows + 31) / 32;
+  for (int64_t blk = static_cast<int64_t>(blockIdx.x) * 4 + warp; blk < nblk;
+       blk += static_cast<int64_t>(gridDim.x) * 4) {
+    const int64_t row0 = blk * 32;
+    const int nrows = rows - row0 < 32 ? static_cast<int>(rows - row0) : 32;
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < nrows; ++r) {
+      sm_lp[warp][r * kPitchW + lane] = __ldg(lp + (row0 + r) * 32 + lane);
+      sm_dy[warp][r * kPitchW + lane] = __ldg(dy + (row0 + r) * 32 + lane);
+    }
+    __syncwarp();
+    if (lane < nrows) {
+      uint32_t* l32 = &sm_lp[warp][lane * kPitchW];
+      uint32_t* d32 = &sm_dy[warp][lane * kPitchW];
+      float sum = 0.f;
+      for (int c = 0; c < 32; ++c) {
+        float2 g;
+        if (bf16) g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d32[c]));
+        else g = __half22float2(*reinterpret_cast<const __half2*>(&d32[c]));
+        sum += (2 * c < n ? g.x : 0.f) + (2 * c + 1 < n ? g.y : 0.f);
+      }
+      for (int c = 0; c < 32; ++c) {
+        float2 g, l;
+        if (bf16) {
+          g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d32[c]));
+          l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l32[c]));
+        } else {
+          g = __half22float2(*reinterpret_cast<const __half2*>(&d32[c]));
+          l = __half22float2(*reinterpret_cast<const __half2*>(&l32[c]));
+        }
+        const float o0 = 2 * c < n ? (g.x - __expf(l.x) * sum) * sc : 0.f;
+        const float o1 = 2 * c + 1 < n ? (g.y - __expf(l.y) * sum) * sc : 0.f;
+        d32[c] = bf16 ? pack_bf16x2(o0, o1) : pack_f16x2_sat(o0, o1);
+      }
+    }
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < nrows; ++r) dz[(row0 + r) * 32 + lane] = sm_dy[warp][r * kPitchW + lane];
   }
 }
 
@@ -141,11 +231,11 @@ extern "C" int pcadv_softmax_head(const pcadv_head_args* a, void* stream) {
   PCADV_CHECK_ARG(!a->probs || a->probs_cols >= a->n, "pcadv_softmax_head: probs_cols < n");
   PCADV_CHECK_ARG(!a->dz || (a->dz_cols >= a->n && a->labels), "pcadv_softmax_head: dz needs labels, dz_cols >= n");
   if (a->rows == 0) return 0;
-  const size_t smem = static_cast<size_t>(8) * 32 * (a->n | 1) * sizeof(float);
+  const size_t smem = static_cast<size_t>(8) * (32 * (a->n | 1) + 32 * kPitchW) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     PCADV_CUDA_OK(cudaFuncSetAttribute(softmax_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       8 * 32 * (kHeadMaxN | 1) * 4));
+                                       8 * (32 * (kHeadMaxN | 1) + 32 * kPitchW) * 4));
     attr_done = true;
   }
   const int64_t nblk = (a->rows + 31) / 32;
@@ -162,6 +252,19 @@ extern "C" int pcadv_logsoftmax_bwd(const void* lp, int32_t lp_dtype, int64_t ld
                                     int32_t dz_cols, void* stream) {
   PCADV_CHECK_ARG(lp && dy && dz && rows >= 0 && n > 0 && dz_cols >= n, "pcadv_logsoftmax_bwd: bad args");
   if (rows == 0) return 0;
+  const bool packed = lp_dtype != PCADV_F32 && dy_dtype == lp_dtype && dz_dtype == lp_dtype && n <= 64 &&
+                      ld_lp == 64 && ld_dy == 64 && ld_dz == 64 && dz_cols == 64 &&
+                      ((reinterpret_cast<uintptr_t>(lp) | reinterpret_cast<uintptr_t>(dy) |
+                        reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
+  if (packed) {
+    int64_t grid = ((rows + 31) / 32 + 3) / 4;
+    if (grid > 148 * 12) grid = 148 * 12;
+    logsoftmax_bwd16_kernel<<<static_cast<unsigned>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t*>(lp), reinterpret_cast<const uint32_t*>(dy), rows, n, scale,
+        reinterpret_cast<uint32_t*>(dz), lp_dtype == PCADV_BF16 ? 1 : 0);
+    PCADV_LAUNCHED();
+    return 0;
+  }
   logsoftmax_bwd_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0,
                           static_cast<cudaStream_t>(stream)>>>(lp, lp_dtype, ld_lp, dy, dy_dtype, ld_dy,
                                                                rows, n, scale, dz, dz_dtype, ld_dz, dz_cols);

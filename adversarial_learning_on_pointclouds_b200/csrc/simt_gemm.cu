@@ -335,37 +335,62 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_arg
   }
   const float* x = reinterpret_cast<const float*>(a.seg[0].ptr);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x / groups;
-  for (int64_t r = tid / groups; r < a.rows; r += stride) {
-    float xv[K];
+  const int gidx = static_cast<int>(tid % groups);
+  // two points per trip: both xyz loads are in flight before either is used.  The trip count is
+  // warp-uniform (bounded by the warp's first point) because the sign-bit words are combined
+  // with full-warp shuffles.
+  const int64_t warp_first = (tid - (threadIdx.x & 31)) / groups;
+  for (int64_t off = 0; warp_first + off < a.rows; off += 2 * stride) {
+    const int64_t r0 = tid / groups + off;
+    float xv[2][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) xv[k] = __ldg(x + r * a.seg[0].ld + k);
-    float v[8];
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * stride;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float acc = b[i];
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc = fmaf(xv[k], w[i][k], acc);
-      v[i] = apply_act(acc, a.act, a.slope);
+      for (int k = 0; k < K; ++k) xv[u][k] = r < a.rows ? __ldg(x + r * a.seg[0].ld + k) : 0.f;
     }
-    if (a.out_dtype == PCADV_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + r * a.ld_out + cg);
-      o[0] = make_float4(v[0], v[1], v[2], v[3]);
-      o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      uint32_t pk[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (a.out_dtype == PCADV_F16) {
-          __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f),
-                                        fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
-          pk[i] = *reinterpret_cast<uint32_t*>(&h);
-        } else {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * stride;
+      const bool r_ok = r < a.rows;                  // uniform over the threads of a point
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float acc = b[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(xv[u][k], w[i][k], acc);
+        v[i] = apply_act(acc, a.act, a.slope);
+      }
+      if (a.out_dtype == PCADV_F32) {
+        if (r_ok) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + r * a.ld_out + cg);
+          o[0] = make_float4(v[0], v[1], v[2], v[3]);
+          o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      } else {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pk[i] = a.out_dtype == PCADV_F16 ? pack_f16x2_sat(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (r_ok)
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + r * a.ld_out + cg) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (a.bits_out) {
+          // sign-bit map (layout in pcadv.h): the four threads that share a 32-column word OR
+          // their 4 + 4 bits together; packed pair i of this thread is pair (gidx % 4) * 4 + i
+          uint32_t wbits = 0u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t m;
+            if (a.out_dtype == PCADV_F16) asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(pk[i]), "r"(0u));
+            else asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(pk[i]), "r"(0u));
+            wbits |= m & (0x00010001u << ((gidx & 3) * 4 + i));
+          }
+          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+          wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+          if (r_ok && (gidx & 3) == 0) a.bits_out[r * a.ld_bits_out + (gidx >> 2)] = wbits;
         }
       }
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + r * a.ld_out + cg) =
-          make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -519,12 +544,15 @@ static bool first_layer_wgrad_eligible(const pcadv_wgrad_args& a) {
 static bool first_layer_eligible(const pcadv_linear_args& a) {
   const int esz = a.out_dtype == PCADV_F32 ? 4 : 2;
   return a.num_seg == 1 && a.seg[0].k >= 1 && a.seg[0].k <= 4 && a.seg[0].dtype == PCADV_F32 &&
-         a.n % 8 == 0 && a.n <= 256 && 256 % (a.n / 8) == 0 && a.out && !a.group_bias && !a.addend && !a.mask &&
+         a.n % 8 == 0 && a.n <= 256 && 256 % (a.n / 8) == 0 && (!a.bits_out || (a.n % 32 == 0 && a.out_dtype != PCADV_F32)) &&
+         !a.mask_bits && a.out && !a.group_bias && !a.addend && !a.mask &&
          !a.out_scale && !a.colmax_key && !a.rowmax_key && (a.ld_out * esz) % 16 == 0 &&
          (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && a.rows >= 1024;
 }
 
 int simt_linear(const pcadv_linear_args& a, cudaStream_t s) {
+  PCADV_CHECK_ARG((!a.bits_out && !a.mask_bits) || first_layer_eligible(a),
+                  "pcadv_linear: on the CUDA-core engine only the first-layer kernel writes sign bits");
   if (first_layer_eligible(a)) {
     const int64_t threads = a.rows * (a.n / 8);
     int64_t blocks = (threads + 255) / 256;
@@ -542,7 +570,7 @@ int simt_linear(const pcadv_linear_args& a, cudaStream_t s) {
   }
   int ktot = 0;
   for (int i = 0; i < a.num_seg; ++i) ktot += a.seg[i].k;
-  if (a.rows <= 1024 && ktot >= 256 && a.out && !a.group_bias && !a.addend && !a.mask && !a.colmax_key &&
+  if (a.rows <= 1024 && ktot >= 1024 && a.out && !a.group_bias && !a.addend && !a.mask && !a.colmax_key &&
       !a.rowmax_key) {
     dim3 grid(static_cast<unsigned>((a.rows + TR - 1) / TR), (a.n + TC - 1) / TC);
     thin_linear_kernel<<<grid, 256, 0, s>>>(a);

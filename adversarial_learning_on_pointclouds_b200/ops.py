@@ -181,8 +181,8 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
     elif mask_bits is not None:
         raise ValueError("mask_bits needs the tensor-core engine and a 16-bit output (pass mask too)")
     if bits_out is not None:
-        if engine != ENGINE_TC or out_dtype == torch.float32 or not want_out:
-            raise ValueError("bits_out needs the tensor-core engine and a 16-bit output")
+        if out_dtype == torch.float32 or not want_out:
+            raise ValueError("bits_out needs a 16-bit output")
         a.bits_out, a.ld_bits_out = C.c_void_p(bits_out.data_ptr()), bits_out.stride(0)
     a.out_scale = _f32(out_scale) if out_scale is not None else None
     out = ckey = rkey = None
@@ -209,8 +209,12 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
 def bits_eligible(prec, segs, w, n):
     """True when a layer can emit / consume the 1-bit activation mask: tensor-core engine,
     16-bit storage, n a multiple of 64."""
-    return prec.engine == ENGINE_TC and prec.act_dtype != torch.float32 and n % 64 == 0 and \
-        tc_eligible(segs, w, n)
+    if prec.engine != ENGINE_TC or prec.act_dtype == torch.float32 or n % 64:
+        return False
+    if len(segs) == 1 and segs[0].shape[1] <= 4 and segs[0].dtype == torch.float32:
+        # the CUDA-core first-layer kernel (Conv1d(3, 64)) writes the map too
+        return n <= 256 and segs[0].shape[0] >= 1024
+    return tc_eligible(segs, w, n)
 
 
 def new_bits(rows, n, device):

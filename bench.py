@@ -340,6 +340,7 @@ def run_cuda(args):
                      "reference-shaped modules + torch losses (trainer.adversarial_seg_step)"),
         "clocks": sampler.summary(),
         "roofline": roofline,
+        "kernel_rooflines": kernel_rooflines(ksum, (Bg + Bn) / 2.0 * N, peaks, args.steps),
         "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in
                                sorted(ksum.items(), key=lambda kv: -kv[1][1])[:args.top_kernels]},
     }
@@ -356,6 +357,50 @@ def run_cuda(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def kernel_rooflines(ksum, points, peaks, steps, top=14):
+    """Achieved HBM GB/s and tensor TFLOP/s of the per-point kernels against the measured peaks,
+    from their call signatures (algorithmic bytes / FLOPs per point: DESIGN.md 4) and their mean
+    launch time (CUDA events on the launching stream).  ``points`` = rows of one launch."""
+    import re
+    out = []
+    for tag, (calls, tot_ms) in ksum.items():
+        m = re.match(r"(linear|wgrad):tc:(?:k(\d+):n(\d+)|n(\d+):k(\d+))(.*)", tag)
+        by = fl = None
+        if m:
+            kind, flags = m.group(1), m.group(6)
+            k = int(m.group(2) or m.group(5))
+            n = int(m.group(3) or m.group(4))
+            fl = 2.0 * k * n
+            if kind == "wgrad":
+                by = 2.0 * (k + n)                                  # dz + x, 16-bit
+            elif "colmax" in flags:
+                by = 2.0 * k                                        # output never stored
+            elif "rowmax" in flags:
+                by = 2.0 * k + 8
+            else:
+                out_b = 4.0 * n if n == 50 else 2.0 * n             # fp32 logits, else 16-bit
+                by = 2.0 * k + out_b + (n / 8.0 if n % 64 == 0 else 0.0)
+                if ":mask" in flags and "maskbits" not in flags:
+                    by += 2.0 * n
+        elif tag == "linear:simt:k3:n64":
+            by, fl = 12.0 + 128.0, 2.0 * 3 * 64
+        elif tag.startswith("softmax_head"):
+            by, fl = 200.0 + (256.0 if tag.endswith("ce") else 128.0) + 8.0, 0.0
+        elif tag == "logsoftmax_bwd":
+            by, fl = 3 * 128.0, 0.0
+        if by is None:
+            continue
+        per_call_s = tot_ms / calls / 1e3
+        gbs = by * points / per_call_s / 1e9
+        tfs = fl * points / per_call_s / 1e12
+        out.append({"kernel": tag, "calls_per_step": calls / steps, "ms_per_call": round(tot_ms / calls, 4),
+                    "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm"], 3),
+                    "tflops": round(tfs, 1), "tensor_frac": round(tfs / peaks["bf16_sustained"], 3),
+                    "ms_per_step": round(tot_ms / steps, 4)})
+    out.sort(key=lambda d: -d["ms_per_step"])
+    return out[:top]
 
 
 def tot_points_per_launch(ksum, Bg, Bn, N):
