@@ -339,6 +339,16 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
     for (int j = 0; j < kMaxVec; ++j)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+    // the touched row of x (mask) and dz: fetched now, used after the run's gathers
+    const int64_t grow = static_cast<int64_t>(g) * a.rows_per_group + row;
+    const uint4* xrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.x) + grow * a.ldx);
+    uint4* drow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.dz_inout) + grow * a.ld_dz);
+    uint4 xr[kMaxVec], dr[kMaxVec];
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nvec) { xr[j] = xrow[v]; dr[j] = drow[v]; }
+    }
     bool more = true;
     while (more) {
       // metadata of the next 32 list entries, one per lane; the run is a prefix of the window
@@ -349,43 +359,37 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
       const unsigned same = __ballot_sync(0xffffffffu, mrow == row);
       const int len = same == 0xffffffffu ? 32 : __ffs(~same) - 1;
       more = len == 32;
-      for (int i = 0; i < len; i += 2) {
-        const int c0 = __shfl_sync(0xffffffffu, mc, i);
-        const float d0 = __shfl_sync(0xffffffffu, mdz, i);
-        const int i1 = i + 1 < len ? i + 1 : i;
-        const int c1 = __shfl_sync(0xffffffffu, mc, i1);
-        const float d1 = i + 1 < len ? __shfl_sync(0xffffffffu, mdz, i1) : 0.f;
-        uint4 r0[kMaxVec], r1[kMaxVec];
+      for (int i = 0; i < len; i += 4) {               // four gathers in flight
+        int cs[4];
+        float ds[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int iu = i + u < len ? i + u : i;
+          cs[u] = __shfl_sync(0xffffffffu, mc, iu);
+          const float d = __shfl_sync(0xffffffffu, mdz, iu);
+          ds[u] = i + u < len ? d : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < kMaxVec; ++j) {
           const int v = lane + 32 * j;
           if (v < nvec) {
-            r0[j] = __ldg(wbase + static_cast<int64_t>(c0) * ldw4 + v);
-            r1[j] = __ldg(wbase + static_cast<int64_t>(c1) * ldw4 + v);
-          }
-        }
+            uint4 rw[4];
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
-          if (lane + 32 * j < nvec) {
-            fma8<kBf16>(r0[j], d0, acc[j]);
-            fma8<kBf16>(r1[j], d1, acc[j]);
+            for (int u = 0; u < 4; ++u) rw[u] = __ldg(wbase + static_cast<int64_t>(cs[u]) * ldw4 + v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fma8<kBf16>(rw[u], ds[u], acc[j]);
           }
         }
       }
       q += len;
     }
     // one read-modify-write of the touched row, through the previous layer's activation mask
-    const int64_t grow = static_cast<int64_t>(g) * a.rows_per_group + row;
-    const uint4* xrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.x) + grow * a.ldx);
-    uint4* drow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.dz_inout) + grow * a.ld_dz);
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
       const int v = lane + 32 * j;
       if (v < nvec) {
-        const uint4 xr = xrow[v];
-        const uint4 dr = drow[v];
-        const uint32_t x4[4] = {xr.x, xr.y, xr.z, xr.w};
-        const uint32_t d4[4] = {dr.x, dr.y, dr.z, dr.w};
+        const uint32_t x4[4] = {xr[j].x, xr[j].y, xr[j].z, xr[j].w};
+        const uint32_t d4[4] = {dr[j].x, dr[j].y, dr[j].z, dr[j].w};
         uint32_t o4[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
