@@ -238,7 +238,7 @@ constexpr int kAddNone = 0, kAddBias = 1, kAddBiasGroup = 2;
 // addend / row-max / output scale.  kAdd: what is added to the accumulator (nothing -- dgrad;
 // bias -- forward layers; bias + per-cloud bias -- fc1).  kMaskBits: multiply by act'(.) read from
 // the forward layer's sign-bit map (dgrad).  Emits the sign-bit map of its own output on request.
-template <int kAct, int kOut, int kAdd, bool kMaskBits>
+template <int kAct, int kOut, int kAdd, bool kMaskBits, bool kRowMax = false>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -333,12 +333,16 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               static_cast<uint32_t>(half * kMaxTileN);
+      float best = -INFINITY;                             // kRowMax: running (max, first column)
+      int best_col = 0;
 #pragma unroll 1
       for (int step = 0; step < steps; ++step) {
         const uint32_t srow = slab0 + slab * kWarpSlabBytes;
-        // the store that last read this slab (two steps ago) is done with it
-        if (lane == 0) bulk_wait_group_read<1>();
-        __syncwarp();
+        if (!kRowMax) {
+          // the store that last read this slab (two steps ago) is done with it
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+        }
         uint32_t raw[2][32];
         tmem_ld32_issue(taddr0 + step * 64, raw[0]);
         tmem_ld32_issue(taddr0 + step * 64 + 32, raw[1]);
@@ -371,6 +375,20 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
               }
             }
           }
+          if (kRowMax) {
+            // max over the row's channels of the PRE-activation value, first column on ties
+            float m = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+            if (m > best) {
+              int jj = 0;
+#pragma unroll
+              for (int j = 31; j >= 0; --j) jj = (v[j] == m) ? j : jj;
+              best = m;
+              best_col = col_base + step * 64 + h * 32 + jj;
+            }
+            continue;
+          }
           if (kAct == PCADV_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -398,6 +416,7 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
           for (int q = 0; q < 4; ++q)
             sts128(srow + (((h * 4 + q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
+        if (kRowMax) continue;
         if (want_bits) sts64(bits_s + (lane * kBitsWords + 2 * step) * 4, obits[0], obits[1]);
         fence_proxy_async();
         __syncwarp();
@@ -406,6 +425,11 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
           bulk_commit_group();
         }
         slab ^= 1;
+      }
+      if (kRowMax && r_ok) {
+        const unsigned long long key = pack_key(best, static_cast<uint32_t>(best_col));
+        if (tiles_n == 1) p.rowmax_key[r] = key;          // the tile holds the whole row
+        else atomicMax(&p.rowmax_key[r], key);
       }
       if (want_bits) {
         // the warp's [32 rows][bn / 32 words] sign-bit tile, consecutive lanes on consecutive
@@ -439,8 +463,12 @@ static RowsKernel pick_lean(int act, int add, bool maskbits) {
   if (act == PCADV_ACT_RELU && add == kAddBias) return tc_rows_lean_kernel<PCADV_ACT_RELU, kOut, kAddBias, false>;
   if (act == PCADV_ACT_RELU && add == kAddBiasGroup) return tc_rows_lean_kernel<PCADV_ACT_RELU, kOut, kAddBiasGroup, false>;
   if (act == PCADV_ACT_LEAKY && add == kAddBias) return tc_rows_lean_kernel<PCADV_ACT_LEAKY, kOut, kAddBias, false>;
+  if (act == PCADV_ACT_NONE && add == kAddNone) return tc_rows_lean_kernel<PCADV_ACT_NONE, kOut, kAddNone, false>;
+  if (act == PCADV_ACT_NONE && add == kAddBias) return tc_rows_lean_kernel<PCADV_ACT_NONE, kOut, kAddBias, false>;
   return nullptr;
 }
+// max over channels only (no stored output): the discriminators' last layer
+static RowsKernel lean_rowmax() { return tc_rows_lean_kernel<PCADV_ACT_NONE, PCADV_F16, kAddBias, false, true>; }
 
 // =====================================================================================
 // kAct: PCADV_ACT_*;  kOut: PCADV_F32 / PCADV_F16 / PCADV_BF16
@@ -819,6 +847,8 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
     lean = out_dt == PCADV_F16 ? pick_lean<PCADV_F16>(a.act, add, p.mask_bits != nullptr)
                                : pick_lean<PCADV_BF16>(a.act, add, p.mask_bits != nullptr);
   }
+  if (!a.out && a.rowmax_key && a.n % 64 == 0 && !a.addend && !a.mask && !a.group_bias && !a.out_scale)
+    lean = lean_rowmax();
   PCADV_CHECK_ARG(lean || (!a.bits_out && !p.mask_bits),
                   "tc_linear: bit masks are only implemented for the lean layer shapes");
   p.tma_mask = (!lean && p.tma_out && a.mask && a.mask_act != PCADV_ACT_NONE && out_dt != PCADV_F32 &&
