@@ -564,6 +564,134 @@ __global__ void __launch_bounds__(256) rowmax_wgrad_kernel(const float* __restri
       if (bias_s[e] != 0.f) atomicAdd(&dbias[e], bias_s[e]);
 }
 
+// Sorted variant for 16-bit y rows (k in {64, 128, 256}): every CTA takes 2048-row chunks, buckets
+// the rows of a chunk by their argmax channel in shared memory (count, scan, fill -- integer
+// atomics only), then the eight warps walk equal slices of the channel-sorted row list with the
+// running channel's sums in registers; a shared-memory float add happens only when the channel
+// changes (<= n + 8 times per chunk instead of once per row and column).
+constexpr int kRwChunk = 2048;
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256) rowmax_wgrad_sorted_kernel(
+    const float* __restrict__ dy, const float* __restrict__ val, const int32_t* __restrict__ idx,
+    int64_t rows, int n, int k, int act, float slope, const uint16_t* __restrict__ yprev, int64_t ld_y,
+    float* dw, int64_t ld_dw, float* dbias) {
+  extern __shared__ float acc_s[];                       // [n * k] + [n] + chunk tables
+  float* bias_s = acc_s + static_cast<size_t>(n) * k;
+  float* s_s = bias_s + n;                               // [kRwChunk]
+  int* cnt = reinterpret_cast<int*>(s_s + kRwChunk);     // [n + 1] starts after the scan
+  int* fillp = cnt + n + 1;                              // [n]
+  uint16_t* ch_s = reinterpret_cast<uint16_t*>(fillp + n);   // [kRwChunk]
+  uint16_t* list_s = ch_s + kRwChunk;                    // [kRwChunk] rows ordered by channel
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int epl = k >> 5;                                // y elements per lane: 2, 4 or 8
+  for (int e = t; e < n * k + n; e += 256) acc_s[e] = 0.f;
+  const int64_t nchunks = (rows + kRwChunk - 1) / kRwChunk;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t base = chunk * kRwChunk;
+    const int m = rows - base < kRwChunk ? static_cast<int>(rows - base) : kRwChunk;
+    __syncthreads();                                     // previous chunk's tables are free
+    for (int c = t; c <= n; c += 256) cnt[c] = 0;
+    __syncthreads();
+    for (int i = t; i < m; i += 256) {
+      const float sv = dy[base + i] * act_grad_from_output(val[base + i], act, slope);
+      const int ch = idx[base + i];
+      s_s[i] = sv;
+      ch_s[i] = static_cast<uint16_t>(ch);
+      if (sv != 0.f) atomicAdd(&cnt[ch], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {                                     // exclusive scan of the n counts
+      const int per = (n + 31) / 32;
+      int local = 0;
+      for (int c = lane * per; c < (lane + 1) * per && c < n; ++c) local += cnt[c];
+      int incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int run = incl - local;
+      for (int c = lane * per; c < (lane + 1) * per && c < n; ++c) {
+        const int v = cnt[c];
+        cnt[c] = run;
+        fillp[c] = run;
+        run += v;
+      }
+      if (lane == 31) cnt[n] = incl;                     // total
+    }
+    __syncthreads();
+    for (int i = t; i < m; i += 256)
+      if (s_s[i] != 0.f) list_s[atomicAdd(&fillp[ch_s[i]], 1)] = static_cast<uint16_t>(i);
+    __syncthreads();
+    const int total = cnt[n];
+    const int q0 = static_cast<int>(static_cast<int64_t>(total) * warp / 8);
+    const int q1 = static_cast<int>(static_cast<int64_t>(total) * (warp + 1) / 8);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    float bsum = 0.f;
+    int cur = -1;
+    auto flush = [&]() {
+      if (cur >= 0) {
+        float* dst = acc_s + static_cast<size_t>(cur) * k + lane * epl;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e < epl) atomicAdd(dst + e, acc[e]);
+        if (lane == 0) atomicAdd(&bias_s[cur], bsum);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      bsum = 0.f;
+    };
+    for (int q = q0; q < q1; q += 4) {
+      int ri[4], chs[4];
+      float sv[4];
+      uint4 yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = q + u < q1;
+        ri[u] = ok ? list_s[q + u] : 0;
+        chs[u] = ok ? ch_s[ri[u]] : -1;
+        sv[u] = ok ? s_s[ri[u]] : 0.f;
+        yv[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
+          const uint16_t* yp = yprev + (base + ri[u]) * ld_y + lane * epl;
+          if (epl == 2) yv[u].x = *reinterpret_cast<const uint32_t*>(yp);
+          else if (epl == 4) { const uint2 v2 = *reinterpret_cast<const uint2*>(yp); yv[u].x = v2.x; yv[u].y = v2.y; }
+          else yv[u] = *reinterpret_cast<const uint4*>(yp);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (chs[u] < 0) continue;
+        if (chs[u] != cur) { flush(); cur = chs[u]; }
+        const uint32_t w4[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          if (2 * e2 < epl) {
+            float2 f;
+            if (kBf16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e2]));
+            else f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e2]));
+            acc[2 * e2] = fmaf(sv[u], f.x, acc[2 * e2]);
+            acc[2 * e2 + 1] = fmaf(sv[u], f.y, acc[2 * e2 + 1]);
+          }
+        }
+        bsum += sv[u];
+      }
+    }
+    flush();
+  }
+  __syncthreads();
+  for (int e = t; e < n * k; e += 256) {
+    const float v = acc_s[e];
+    if (v != 0.f && dw) atomicAdd(&dw[static_cast<int64_t>(e / k) * ld_dw + (e % k)], v);
+  }
+  if (dbias)
+    for (int e = t; e < n; e += 256)
+      if (bias_s[e] != 0.f) atomicAdd(&dbias[e], bias_s[e]);
+}
+
 __global__ void amax_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld,
                             unsigned int* ws) {
   float m = 0.f;
@@ -805,6 +933,34 @@ extern "C" int pcadv_rowmax_wgrad(const float* dy, const float* val, const int32
     PCADV_CUDA_OK(cudaFuncSetAttribute(rowmax_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
     attr = 200 * 1024;
+  }
+  if (y_dtype != PCADV_F32 && (k == 64 || k == 128 || k == 256) && n <= 1024 && ld_y % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(yprev) & 15) == 0) {
+    const size_t smem2 = smem + kRwChunk * sizeof(float) + (2 * static_cast<size_t>(n) + 1) * sizeof(int) +
+                         2 * kRwChunk * sizeof(uint16_t) + 16;
+    if (smem2 <= 200 * 1024) {
+      static bool attr2 = false;
+      if (!attr2) {
+        PCADV_CUDA_OK(cudaFuncSetAttribute(rowmax_wgrad_sorted_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PCADV_CUDA_OK(cudaFuncSetAttribute(rowmax_wgrad_sorted_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr2 = true;
+      }
+      int64_t blocks2 = (rows + kRwChunk - 1) / kRwChunk;
+      const int64_t per_sm = (200 * 1024) / static_cast<int64_t>(smem2 + 1024);
+      const int64_t cap2 = 148 * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+      if (blocks2 > cap2) blocks2 = cap2;
+      const uint16_t* y16 = reinterpret_cast<const uint16_t*>(yprev);
+      if (y_dtype == PCADV_BF16)
+        rowmax_wgrad_sorted_kernel<true><<<static_cast<unsigned>(blocks2), 256, smem2, static_cast<cudaStream_t>(stream)>>>(
+            dy, val, idx, rows, n, k, act, slope, y16, ld_y, dw, ld_dw, dbias);
+      else
+        rowmax_wgrad_sorted_kernel<false><<<static_cast<unsigned>(blocks2), 256, smem2, static_cast<cudaStream_t>(stream)>>>(
+            dy, val, idx, rows, n, k, act, slope, y16, ld_y, dw, ld_dw, dbias);
+      PCADV_LAUNCHED();
+      return 0;
+    }
   }
   const int64_t total = rows * (k / 8);
   int64_t blocks = (total + 255) / 256;
