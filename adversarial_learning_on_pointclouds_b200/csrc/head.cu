@@ -133,6 +133,79 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
   }
 }
 
+// Packed path (n <= 64 classes, contiguous fp32 logits rows with an even n, 16-bit [rows, 64]
+// outputs): lane = column pair, a warp walks rows four at a time; max / sum over the row are
+// warp shuffles, every load and store is one fully coalesced row segment.
+template <bool kBf16>
+__global__ void __launch_bounds__(256) softmax_head_rows_kernel(const pcadv_head_args a) {
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = a.n;
+  const bool col_ok = 2 * lane < n;                       // n is even: both columns of the pair exist
+  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  uint32_t* probs = reinterpret_cast<uint32_t*>(a.probs);
+  uint32_t* dz = reinterpret_cast<uint32_t*>(a.dz);
+  float loss = 0.f;
+  for (int64_t r0 = gwarp * 4; r0 < a.rows; r0 += nwarps * 4) {
+    float2 t[4];
+    int label[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u;
+      t[u] = make_float2(-INFINITY, -INFINITY);
+      label[u] = -1;
+      if (r < a.rows) {
+        if (col_ok) t[u] = __ldg(reinterpret_cast<const float2*>(a.logits + r * n) + lane);
+        if (a.labels) label[u] = static_cast<int>(__ldg(a.labels + r));
+      }
+    }
+    float m[4], s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = fmaxf(t[u].x, t[u].y);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = col_ok ? __expf(t[u].x - m[u]) + __expf(t[u].y - m[u]) : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u;
+      if (r >= a.rows) continue;
+      const float lse = m[u] + __logf(s[u]);
+      const float l0 = col_ok ? t[u].x - lse : 0.f, l1 = col_ok ? t[u].y - lse : 0.f;
+      const float p0 = col_ok ? __expf(l0) : 0.f, p1 = col_ok ? __expf(l1) : 0.f;
+      if (label[u] == 2 * lane) loss -= l0;
+      else if (label[u] == 2 * lane + 1) loss -= l1;
+      if (probs) {
+        const float o0 = a.mode == PCADV_HEAD_LSM ? l0 : p0, o1 = a.mode == PCADV_HEAD_LSM ? l1 : p1;
+        probs[r * 32 + lane] = kBf16 ? pack_bf16x2(o0, o1) : pack_f16x2_sat(o0, o1);
+      }
+      if (dz) {
+        const float d0 = col_ok ? a.dz_gain * (p0 - (label[u] == 2 * lane ? 1.f : 0.f)) : 0.f;
+        const float d1 = col_ok ? a.dz_gain * (p1 - (label[u] == 2 * lane + 1 ? 1.f : 0.f)) : 0.f;
+        dz[r * 32 + lane] = kBf16 ? pack_bf16x2(d0, d1) : pack_f16x2_sat(d0, d1);
+      }
+    }
+  }
+  if (a.loss_sum) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) red[warp] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float sum = 0.f;
+      for (int w = 0; w < 8; ++w) sum += red[w];
+      atomicAdd(a.loss_sum, sum);
+    }
+  }
+}
+
 // Packed path ([rows, 64] 16-bit lp / dy / dz with contiguous rows): a warp stages its 32 rows of
 // lp and dy with coalesced 16-byte loads, thread = row computes in place, coalesced store.
 __global__ void __launch_bounds__(128) logsoftmax_bwd16_kernel(const uint32_t* __restrict__ lp,
@@ -231,6 +304,25 @@ extern "C" int pcadv_softmax_head(const pcadv_head_args* a, void* stream) {
   PCADV_CHECK_ARG(!a->probs || a->probs_cols >= a->n, "pcadv_softmax_head: probs_cols < n");
   PCADV_CHECK_ARG(!a->dz || (a->dz_cols >= a->n && a->labels), "pcadv_softmax_head: dz needs labels, dz_cols >= n");
   if (a->rows == 0) return 0;
+  {
+    auto packed16 = [](const void* p, int64_t ld, int dtype, int cols) {
+      return p == nullptr || (dtype != PCADV_F32 && cols == 64 && ld == 64 && (reinterpret_cast<uintptr_t>(p) & 3) == 0);
+    };
+    const bool same_dt = !a->probs || !a->dz || a->probs_dtype == a->dz_dtype;
+    if (a->n <= 64 && a->n % 2 == 0 && a->ld == a->n && (reinterpret_cast<uintptr_t>(a->logits) & 7) == 0 &&
+        (a->probs || a->dz) && packed16(a->probs, a->ld_probs, a->probs_dtype, a->probs_cols) &&
+        packed16(a->dz, a->ld_dz, a->dz_dtype, a->dz_cols) && same_dt) {
+      const int dt = a->probs ? a->probs_dtype : a->dz_dtype;
+      int64_t grid = (a->rows + 31) / 32;
+      if (grid > 148 * 8) grid = 148 * 8;
+      if (dt == PCADV_BF16)
+        softmax_head_rows_kernel<true><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+      else
+        softmax_head_rows_kernel<false><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+      PCADV_LAUNCHED();
+      return 0;
+    }
+  }
   const size_t smem = static_cast<size_t>(8) * (32 * (a->n | 1) + 32 * kPitchW) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
