@@ -12,6 +12,7 @@
 // ~48 KB) so narrow layers do not pay one barrier round trip per 64 rows.  The bias gradient
 // and the per-cloud bias gradient (column sums of dz) are taken from the dz boxes in flight by
 // the otherwise idle epilogue warps.
+#include <stdlib.h>
 #include "tc_pipeline.cuh"
 
 namespace pcadv {
@@ -348,7 +349,12 @@ int tc_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
   }
   p.seg_box0[a.num_seg] = boxes;
   // N tiles: as few as possible (each one re-reads dz), boxes spread evenly over them
-  p.tiles_n = (boxes + kMaxBoxes - 1) / kMaxBoxes;
+  int max_boxes = kMaxBoxes;
+  if (const char* e = getenv("PCADV_WGRAD_MAXBOXES")) {     // tuning aid
+    const int v = atoi(e);
+    if (v >= 1 && v <= kMaxBoxes) max_boxes = v;
+  }
+  p.tiles_n = (boxes + max_boxes - 1) / max_boxes;
   // the bias MMA needs 16 accumulator columns next to the first tile's: at most 7 boxes there
   if (a.dbias && (boxes + p.tiles_n - 1) / p.tiles_n > kMaxBoxes - 1) ++p.tiles_n;
   PCADV_CHECK_ARG(p.tiles_n <= kMaxNTiles, "tc_wgrad: K too large (%d boxes)", boxes);

@@ -85,9 +85,22 @@ class ClockSampler(threading.Thread):
                     samples=len(sm))
 
 
+def synthetic_inputs(B, N, seed):
+    """The synthetic batch of SURVEY.md 8c, drawn in this order from one generator: pts U[-1,1)^3,
+    y in [0,40), seg in [0,50), shape in [0,16).  (Kept here so that the CUDA arm imports nothing
+    from oracle/; tests/test_oracle_golden.py checks it against the oracle's generator.)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(B, N, 3, generator=g) * 2 - 1
+    y = torch.randint(0, 40, (B,), generator=g)
+    seg = torch.randint(0, 50, (B, N), generator=g)
+    shp = torch.randint(0, 16, (B,), generator=g)
+    cls = torch.nn.functional.one_hot(shp, 16).to(torch.float32).view(B, 1, 16)
+    return pts, y, seg, cls
+
+
 def synthetic_batches(Bg, Bn, N, rank):
     """Synthetic ShapeNet-part-shaped clouds: seeds 1234 / 4321 (+rank)."""
-    from oracle.pointnet_oracle import synthetic_inputs
     pts, _, seg, cls = synthetic_inputs(Bg, N, 1234 + 1000 * rank)
     pts2, _, _, cls2 = synthetic_inputs(Bn, N, 4321 + 1000 * rank)
     return (pts, cls, seg), (pts2, cls2)

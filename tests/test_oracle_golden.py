@@ -221,3 +221,14 @@ def test_trainer_seg_step(golden):
         assert_summary_close(v, G["g_after"][k], 1e-6, "g_after:" + k)
     for k, v in dp.items():
         assert_summary_close(v, G["d_after"][k], 1e-6, "d_after:" + k)
+
+
+def test_bench_synthetic_inputs_match_the_oracle_generator():
+    """bench.py carries its own copy of the SURVEY 8c input recipe (its CUDA arm must not import
+    oracle/); it has to draw exactly what the oracle's generator draws."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle.pointnet_oracle import synthetic_inputs
+    for a, b in zip(bench.synthetic_inputs(3, 17, 1234), synthetic_inputs(3, 17, 1234)):
+        assert torch.equal(a, b)
