@@ -119,3 +119,34 @@ def test_tc_bit_masks(dtype, rows, k, n, act):
     b, _, _ = ops.linear([dz], w2, mask=y, mask_act=act, mask_slope=0.2, out_dtype=dtype, engine=ENGINE_TC,
                          mask_bits=bits)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("rows", [129, 389, 1000, 4133])
+def test_caller_buffers_are_not_overrun(rows):
+    """Guard words around the caller-provided buffers (sign-bit map, dW, dbias, packed head
+    outputs) stay untouched for ragged row counts."""
+    dtype = torch.float16
+    k, n = 64, 128
+    x = _rand((rows, k), 31, dtype)
+    w = _rand((n, k), 32, dtype, 0.1)
+    guard = 64
+    raw = torch.full((rows * (n // 32) + 2 * guard,), 0x5A5A5A5A, dtype=torch.int32, device=DEV)
+    bits = raw[guard:guard + rows * (n // 32)].view(rows, n // 32)
+    ops.linear([x], w, bias=_rand((n,), 33, torch.float32), act=ACT_RELU, out_dtype=dtype, engine=ENGINE_TC,
+               bits_out=bits)
+    assert (raw[:guard] == 0x5A5A5A5A).all() and (raw[guard + rows * (n // 32):] == 0x5A5A5A5A).all()
+    # wgrad into a guarded dW / dbias
+    dz = _rand((rows, n), 34, dtype)
+    rawf = torch.full((n * k + n + 2 * guard,), 7.25, dtype=torch.float32, device=DEV)
+    dw = rawf[guard:guard + n * k].view(n, k)
+    db = rawf[guard + n * k:guard + n * k + n]
+    dw.zero_(); db.zero_()
+    ops.wgrad(dz, [x], dw=dw, dbias=db, engine=ENGINE_TC)
+    assert (rawf[:guard] == 7.25).all() and (rawf[guard + n * k + n:] == 7.25).all()
+    assert rel_err(dw, dz.double().t() @ x.double()) < 1e-5
+    assert rel_err(db, dz.double().sum(0)) < 1e-5
+    # packed head outputs are allocated by ops.softmax_head itself; check the values at the ragged end
+    logits = _rand((rows, 50), 35, torch.float32) * 3
+    lp, _ = ops.softmax_head(logits, ops.HEAD_LSM, out_dtype=dtype, cols=64)
+    assert rel_err(lp[:, :50], torch.log_softmax(logits.double(), 1)) < 2e-3
+    assert lp[:, 50:].abs().max().item() == 0
