@@ -141,31 +141,36 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
   const uint32_t tmem_base = st->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const WorkItem it = decode_work(p, w);
-        const int sub_bytes = (2 + it.nb) * kBoxBytes;
-        const uint32_t stage_tx = static_cast<uint32_t>(sub_bytes * subs);
-        for (int64_t r = it.r0; r < it.r1; r += p.stage_rows) {
-          mbar_wait_backoff(&st->empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&st->full[stage], stage_tx);
-          for (int sb = 0; sb < subs; ++sb) {
-            uint8_t* sa = stages + stage * p.stage_bytes + sb * sub_bytes;
-            const int32_t rr = static_cast<int32_t>(r + sb * box_rows);   // rows >= p.rows: zero fill
-            tma_load_2d(sa, &maps.w, &st->full[stage], it.tm * kTileM, rr);
-            tma_load_2d(sa + kBoxBytes, &maps.w, &st->full[stage], it.tm * kTileM + 64, rr);
-            int s = 0;
-            for (int b = 0; b < it.nb; ++b) {
-              const int gb = it.box0 + b;
-              while (gb >= p.seg_box0[s + 1]) ++s;
-              tma_load_2d(sa + (2 + b) * kBoxBytes, &maps.act[s], &st->full[stage],
-                          (gb - p.seg_box0[s]) * 64, rr);
-            }
+    // TMA producer: the whole warp.  A stage is up to ~20 box loads and one thread issues a
+    // tensor copy every ~140 ns, which would cap the pipeline below the MMA rate; lane l issues
+    // box l of the stage instead.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const WorkItem it = decode_work(p, w);
+      const int per_sub = 2 + it.nb;
+      const int sub_bytes = per_sub * kBoxBytes;
+      const int nloads = per_sub * subs;
+      const uint32_t stage_tx = static_cast<uint32_t>(sub_bytes * subs);
+      for (int64_t r = it.r0; r < it.r1; r += p.stage_rows) {
+        mbar_wait_backoff(&st->empty[stage], phase ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&st->full[stage], stage_tx);
+        __syncwarp();
+        for (int l = lane; l < nloads; l += 32) {
+          const int sb = l / per_sub, b = l - sb * per_sub;
+          uint8_t* dst = stages + stage * p.stage_bytes + sb * sub_bytes + b * kBoxBytes;
+          const int32_t rr = static_cast<int32_t>(r + sb * box_rows);   // rows >= p.rows: zero fill
+          if (b < 2) {
+            tma_load_2d(dst, &maps.w, &st->full[stage], it.tm * kTileM + b * 64, rr);
+          } else {
+            const int gb = it.box0 + b - 2;
+            int sg = 0;
+            while (gb >= p.seg_box0[sg + 1]) ++sg;
+            tma_load_2d(dst, &maps.act[sg], &st->full[stage], (gb - p.seg_box0[sg]) * 64, rr);
           }
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -366,6 +371,9 @@ int tc_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
   // wide N tiles take 32-row boxes so that the ring still has >= 4 stages to hide the load
   // latency behind the MMAs; narrow ones put several 64-row sub-chunks into one stage
   p.box_rows = 64;
+  if (const char* e = getenv("PCADV_WGRAD_BOXROWS")) {      // tuning aid
+    if (atoi(e) == 32 && max_nb > 4) p.box_rows = 32;
+  }
   if (int rc = encode_tmap_2d(&maps.w, a.dz, dt, a.rows, a.n, a.ld_dz, 64, p.box_rows)) return rc;
   for (int i = 0; i < a.num_seg; ++i)
     if (int rc = encode_tmap_2d(&maps.act[i], a.seg[i].ptr, dt, a.rows, a.seg[i].k, a.seg[i].ld, 64, p.box_rows))

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import torch
 
 from adversarial_learning_on_pointclouds_b200 import ops
-from adversarial_learning_on_pointclouds_b200.ops import ACT_RELU, ENGINE_TC, ENGINE_SIMT
+from adversarial_learning_on_pointclouds_b200.ops import ACT_NONE, ACT_RELU, ENGINE_TC, ENGINE_SIMT
 
 DEV = "cuda"
 
@@ -31,7 +31,8 @@ def cases(P, N):
             rowmax=False, want_out=True, gb=False, bits=False, maskbits=False):
         segs = [r16((P, k)) for k in ks]
         w = r16((n, sum(ks)), 0.05)
-        kw = dict(bias=torch.randn(n, device=DEV) if bias else None, act=ACT_RELU, out_dtype=out_dtype,
+        kw = dict(bias=torch.randn(n, device=DEV) if bias else None,
+                  act=ACT_NONE if (maskbits or mask) else ACT_RELU, out_dtype=out_dtype,
                   engine=ENGINE_TC, colmax=colmax, rowmax=rowmax, want_out=want_out,
                   rows_per_group=N if (colmax or gb) else 0)
         if mask:
