@@ -331,8 +331,8 @@ def run_cuda(args):
                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 points from
-                    # profiles/r01_ncu_full_conv6max_tc_colmax_kernel.csv (algorithmic: 1.074e9)
-                    "traffic": 1.0878e9 if (Bg + Bn) // 2 * N == (1 << 20) else None,
+                    # profiles/r01c_ncu_full_conv6max_r1c.csv (algorithmic: 1.074e9)
+                    "traffic": 1.0898e9 if (Bg + Bn) // 2 * N == (1 << 20) else None,
                     "traffic_unit": "bytes per launch (ncu --set full, round 1)",
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     "launch_ms": per_launch_s * 1e3, "share_of_step": tot_ms / ms_eager,
