@@ -261,64 +261,49 @@ def point_mlp(prec, x, layers, acts, reduce=None, group=0, tap=None, group_bias=
     return PointMLPFunction.apply(prec, MLPSpec(acts, reduce, group, tap, box), x, group_bias, *params)
 
 
+_TNET_MAX_K = 128
+
+
 class BmmFunction(torch.autograd.Function):
     """y[b] = x[b] @ T[b]: torch.bmm(x^T, trans) of models/pointnet.py:120-122 /
-    :231 / :238 on point-major x [B, N, k] (fp32) and T [B, k, k]."""
+    :231 / :238 on point-major x [B, N, k] (fp32) and T [B, k, k] -- one batched kernel per
+    direction (``pcadv_bmm`` / ``pcadv_bmm_tgrad``)."""
 
     @staticmethod
     def forward(ctx, x, trans):
         B, N, k = x.shape
+        if k > _TNET_MAX_K:
+            raise ValueError("T-Net transforms are implemented for k <= %d" % _TNET_MAX_K)
         x = x.contiguous().float()
         trans = trans.contiguous().float()
-        y = torch.empty_like(x)
-        for b in range(B):
-            wt = trans[b].t().contiguous()                  # out[r, c] = sum_k x[r, k] T[k, c]
-            y[b], _, _ = ops.linear([x[b]], wt, engine=ENGINE_SIMT)
         ctx.save_for_backward(x, trans)
-        return y
+        return ops.bmm(x, trans)
 
     @staticmethod
     def backward(ctx, dy):
         x, trans = ctx.saved_tensors
-        B, N, k = x.shape
         dy = dy.contiguous().float()
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dt = torch.zeros_like(trans) if ctx.needs_input_grad[1] else None
-        for b in range(B):
-            if dx is not None:                              # dx = dy @ T^T
-                dx[b], _, _ = ops.linear([dy[b]], trans[b], engine=ENGINE_SIMT)
-            if dt is not None:                              # dT[k, c] = sum_r x[r, k] dy[r, c]
-                ops.wgrad(x[b], [dy[b]], dw=dt[b])
+        dx = ops.bmm(dy, trans, transpose_t=True) if ctx.needs_input_grad[0] else None   # dy @ T^T
+        dt = ops.bmm_tgrad(x, dy) if ctx.needs_input_grad[1] else None                   # x^T @ dy
         return dx, dt
 
 
 class RegularizerFunction(torch.autograd.Function):
-    """mean_b || T T^T - I ||_F (models/pointnet.py:345-353)."""
+    """mean_b || T T^T - I ||_F (models/pointnet.py:345-353): one CTA per cloud forward
+    (``pcadv_ortho_reg``) and backward (``pcadv_ortho_reg_bwd``)."""
 
     @staticmethod
     def forward(ctx, trans):
-        B, d, _ = trans.shape
         t = trans.contiguous().float()
-        diff = torch.empty_like(t)
-        eye = torch.eye(d, dtype=torch.float32, device=t.device)
-        for b in range(B):                                  # (T T^T)[i, j] = sum_k T[i,k] T[j,k]
-            m, _, _ = ops.linear([t[b]], t[b], engine=ENGINE_SIMT)
-            diff[b] = m - eye
-        norms = diff.reshape(B, -1).norm(dim=1)
+        diff, norms = ops.ortho_reg(t)
         ctx.save_for_backward(t, diff, norms)
         return norms.mean()
 
     @staticmethod
     def backward(ctx, dloss):
         t, diff, norms = ctx.saved_tensors
-        B = t.shape[0]
-        # d||M||_F / dM = M / ||M||;  M = T T^T - I  =>  dT = (G + G^T) T with G = dM
-        G = diff / norms.clamp_min(1e-30).view(B, 1, 1) * (dloss / B)
-        dT = torch.empty_like(t)
-        for b in range(B):
-            sym = (G[b] + G[b].t()).contiguous()
-            dT[b], _, _ = ops.linear([sym], t[b].t().contiguous(), engine=ENGINE_SIMT)
-        return dT
+        # d||M||_F / dM = M / ||M||;  M = T T^T - I symmetric  =>  dT = 2 (dloss / (B ||M||)) M T
+        return ops.ortho_reg_bwd(diff, t, norms, dloss.contiguous().float())
 
 
 __all__ = ["MLPSpec", "PointMLPFunction", "point_mlp", "BmmFunction", "RegularizerFunction",

@@ -439,6 +439,47 @@ def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None)
     return dz
 
 
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError("expected a contiguous fp32 CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def bmm(x, trans, transpose_t=False):
+    """y[b] = x[b] @ T[b] (or @ T[b]^T) for x [B, N, k], T [B, k, k] fp32: see ``pcadv_bmm``."""
+    B, N, k = x.shape
+    y = torch.empty_like(x)
+    _call("bmm:k%d" % k, _lib.lib().pcadv_bmm, _f32c(x), _f32c(trans), _f32c(y), B, N, k,
+          1 if transpose_t else 0, _stream())
+    return y
+
+
+def bmm_tgrad(x, dy):
+    """dT[b] = x[b]^T @ dy[b] for x, dy [B, N, k] fp32: see ``pcadv_bmm_tgrad``."""
+    B, N, k = x.shape
+    dT = torch.zeros((B, k, k), dtype=torch.float32, device=x.device)
+    _call("bmm_tgrad:k%d" % k, _lib.lib().pcadv_bmm_tgrad, _f32c(x), _f32c(dy), _f32c(dT), B, N, k, _stream())
+    return dT
+
+
+def ortho_reg(trans):
+    """(diff [B, d, d] = T T^T - I, norms [B] = ||diff||_F): see ``pcadv_ortho_reg``."""
+    B, d, _ = trans.shape
+    diff = torch.empty_like(trans)
+    norms = torch.empty((B,), dtype=torch.float32, device=trans.device)
+    _call("ortho_reg:d%d" % d, _lib.lib().pcadv_ortho_reg, _f32c(trans), B, d, _f32c(diff), _f32c(norms), _stream())
+    return diff, norms
+
+
+def ortho_reg_bwd(diff, trans, norms, dloss):
+    """dT of mean_b ||T T^T - I||_F: see ``pcadv_ortho_reg_bwd``.  dloss: 0-d / 1-element fp32 tensor."""
+    B, d, _ = trans.shape
+    dT = torch.empty_like(trans)
+    _call("ortho_reg_bwd:d%d" % d, _lib.lib().pcadv_ortho_reg_bwd, _f32c(diff), _f32c(trans), _f32c(norms),
+          _f32c(dloss.reshape(1)), B, d, _f32c(dT), _stream())
+    return dT
+
+
 def transpose(src, out_dtype=None):
     """dst[c, r] = src[r, c] (weight matrices only)."""
     p, ld, dt = _mat(src)

@@ -269,6 +269,28 @@ int pcadv_logsoftmax_bwd(const void* lp, int32_t lp_dtype, int64_t ld_lp, const 
                          int32_t dy_dtype, int64_t ld_dy, int64_t rows, int32_t n, const float* scale,
                          void* dz, int32_t dz_dtype, int64_t ld_dz, int32_t dz_cols, void* stream);
 
+/*
+ * T-Net transforms (fp32, k <= 128), one launch per op instead of one torch.bmm per cloud.
+ *   pcadv_bmm:       y[g, r, :] = x[g, r, :] @ T[g]  (transpose_t = 0)  or  @ T[g]^T  (= 1, the backward dx)
+ *                    -- torch.bmm(x^T, trans) at models/pointnet.py:120-122, :231, :238
+ *   pcadv_bmm_tgrad: dT[g] += x[g]^T @ dy[g]          (caller zero-fills dT)
+ * x, y, dy: [groups, rows_per_group, k] contiguous; T, dT: [groups, k, k] contiguous.
+ */
+int pcadv_bmm(const float* x, const float* T, float* y, int32_t groups, int64_t rows_per_group, int32_t k,
+              int32_t transpose_t, void* stream);
+int pcadv_bmm_tgrad(const float* x, const float* dy, float* dT, int32_t groups, int64_t rows_per_group,
+                    int32_t k, void* stream);
+
+/*
+ * feature_transform_regularizer (models/pointnet.py:345-353), one CTA per cloud:
+ *   pcadv_ortho_reg:     diff[g] = T[g] T[g]^T - I,  norms[g] = ||diff[g]||_F     (loss = mean_g norms[g])
+ *   pcadv_ortho_reg_bwd: dT[g] = (2 * (*dloss) / (groups * norms[g])) * diff[g] @ T[g]
+ * T, diff, dT: [groups, d, d] fp32 contiguous, d <= 128; dloss: device scalar.
+ */
+int pcadv_ortho_reg(const float* T, int32_t groups, int32_t d, float* diff, float* norms, void* stream);
+int pcadv_ortho_reg_bwd(const float* diff, const float* T, const float* norms, const float* dloss,
+                        int32_t groups, int32_t d, float* dT, void* stream);
+
 /* dst[c, r] = src[r, c] with conversion: builds the [k, n] copy of a weight
  * matrix that dgrad consumes. */
 int pcadv_transpose(const void* src, int32_t src_dtype, int64_t ld_src, int32_t rows, int32_t cols,

@@ -533,6 +533,26 @@ def test_fused_adversarial_step_bf16():
         assert rel_err(v.grad, gp[k].grad) < 0.15, (k, rel_err(v.grad, gp[k].grad))
 
 
+@pytest.mark.parametrize("B,N,k", [(3, 100, 3), (2, 257, 64), (4, 1000, 128), (1, 5, 7)])
+def test_tnet_bmm_and_regulariser_kernels(B, N, k):
+    """pcadv_bmm / pcadv_bmm_tgrad / pcadv_ortho_reg(_bwd) against torch autograd (fp64)."""
+    from adversarial_learning_on_pointclouds_b200.models._mlp import BmmFunction, RegularizerFunction
+    x = _rand((B, N, k), 41).to(DEV).requires_grad_(True)
+    T = (_rand((B, k, k), 42) * 0.3 + torch.eye(k, device=DEV)).requires_grad_(True)
+    y = BmmFunction.apply(x, T)
+    reg = RegularizerFunction.apply(T)
+    wy = _rand((B, N, k), 43).to(DEV)
+    (3.0 * reg + (y * wy).sum()).backward()
+    xd, Td = x.detach().double().requires_grad_(True), T.detach().double().requires_grad_(True)
+    yd = torch.bmm(xd, Td)
+    I = torch.eye(k, dtype=torch.float64, device=DEV)[None]
+    regd = torch.mean(torch.norm(torch.bmm(Td, Td.transpose(2, 1)) - I, dim=(1, 2)))
+    (3.0 * regd + (yd * wy.double()).sum()).backward()
+    assert rel_err(y, yd) < 1e-5 and abs(reg.item() - regd.item()) < 1e-5 * max(1.0, abs(regd.item()))
+    assert rel_err(x.grad, xd.grad) < 1e-5
+    assert rel_err(T.grad, Td.grad) < 2e-5
+
+
 def test_launch_counter_counts():
     before = pkg._lib.launch_count()
     x = _rand((256, 64), 1)
