@@ -14,7 +14,8 @@ namespace pcadv {
 namespace {
 
 constexpr int kTnMaxK = 128;
-constexpr int kBmmRows = 64;                 // rows of x per CTA
+constexpr int kBmmRows = 64;                 // rows of x per tile
+constexpr int kBmmTiles = 8;                 // tiles per CTA (T[b] is staged once for all of them)
 
 // grid (ceil(N / 64), B); 256 threads = 16 row groups (4 rows) x 16 column groups (<= 8 columns)
 __global__ void __launch_bounds__(256) bmm_kernel(const float* __restrict__ x, const float* __restrict__ T,
@@ -23,21 +24,24 @@ __global__ void __launch_bounds__(256) bmm_kernel(const float* __restrict__ x, c
   float* Ts = sm;                                        // [k][k + 1]   Ts[j][c] = T_eff[j, c]
   float* xs = sm + k * (k + 1);                          // [64][k + 1]
   const int b = blockIdx.y, t = threadIdx.x;
-  const int n0 = blockIdx.x * kBmmRows;
   const float* Tb = T + static_cast<int64_t>(b) * k * k;
   for (int e = t; e < k * k; e += 256) {
     const int j = e / k, c = e - j * k;
     Ts[j * (k + 1) + c] = transpose_t ? Tb[c * k + j] : Tb[e];
   }
+  const int ty = t >> 4, tx = t & 15;
+  const int cpt = (k + 15) / 16;                         // columns per thread (<= 8)
+  for (int tile = 0; tile < kBmmTiles; ++tile) {
+  const int n0 = (blockIdx.x * kBmmTiles + tile) * kBmmRows;
+  if (n0 >= N) break;
   const float* xb = x + (static_cast<int64_t>(b) * N + n0) * k;
   const int rows = N - n0 < kBmmRows ? N - n0 : kBmmRows;
+  __syncthreads();                                       // previous tile's readers are done
   for (int e = t; e < rows * k; e += 256) {
     const int r = e / k, j = e - r * k;
     xs[r * (k + 1) + j] = xb[e];
   }
   __syncthreads();
-  const int ty = t >> 4, tx = t & 15;
-  const int cpt = (k + 15) / 16;                         // columns per thread (<= 8)
   float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -65,15 +69,18 @@ __global__ void __launch_bounds__(256) bmm_kernel(const float* __restrict__ x, c
       if (c < cpt && col < k) yb[r * k + col] = acc[i][c];
     }
   }
+  }
 }
+
+constexpr int kTgChunk = 64;                 // rows staged per trip
 
 // grid (splits, B); each CTA reduces a row range of cloud b into a k x k tile (8 x 8 per thread
 // for k = 128) and adds it into dT[b] with fp32 atomics
 __global__ void __launch_bounds__(256) bmm_tgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                         float* __restrict__ dT, int N, int k, int rows_per_split) {
   extern __shared__ float sm[];
-  float* xs = sm;                                        // [16][k]
-  float* ds = sm + 16 * k;                               // [16][k]
+  float* xs = sm;                                        // [kTgChunk][k]
+  float* ds = sm + kTgChunk * k;                         // [kTgChunk][k]
   const int b = blockIdx.y, t = threadIdx.x;
   const int r0 = blockIdx.x * rows_per_split;
   const int r1 = r0 + rows_per_split < N ? r0 + rows_per_split : N;
@@ -86,16 +93,16 @@ __global__ void __launch_bounds__(256) bmm_tgrad_kernel(const float* __restrict_
     for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
   const float* xb = x + static_cast<int64_t>(b) * N * k;
   const float* db = dy + static_cast<int64_t>(b) * N * k;
-  for (int r = r0; r < r1; r += 16) {
-    const int rows = r1 - r < 16 ? r1 - r : 16;
+  for (int r = r0; r < r1; r += kTgChunk) {
+    const int rows = r1 - r < kTgChunk ? r1 - r : kTgChunk;
     __syncthreads();
-    for (int e = t; e < 16 * k; e += 256) {
+    for (int e = t; e < kTgChunk * k; e += 256) {
       const bool ok = e < rows * k;
       xs[e] = ok ? xb[static_cast<int64_t>(r) * k + e] : 0.f;
       ds[e] = ok ? db[static_cast<int64_t>(r) * k + e] : 0.f;
     }
     __syncthreads();
-    for (int rr = 0; rr < 16; ++rr) {
+    for (int rr = 0; rr < kTgChunk; ++rr) {
       float xv[8], dv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) xv[i] = (i < per && ty + 16 * i < k) ? xs[rr * k + ty + 16 * i] : 0.f;
@@ -206,7 +213,7 @@ extern "C" int pcadv_bmm(const float* x, const float* T, float* y, int32_t group
   if (groups == 0 || rows_per_group == 0) return 0;
   const size_t smem = (static_cast<size_t>(k) * (k + 1) + kBmmRows * (k + 1)) * sizeof(float);
   if (int rc = set_smem(reinterpret_cast<const void*>(bmm_kernel), smem)) return rc;
-  dim3 grid(static_cast<unsigned>((rows_per_group + kBmmRows - 1) / kBmmRows), groups);
+  dim3 grid(static_cast<unsigned>((rows_per_group + kBmmRows * kBmmTiles - 1) / (kBmmRows * kBmmTiles)), groups);
   bmm_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, T, y, static_cast<int>(rows_per_group),
                                                                      k, transpose_t);
   PCADV_LAUNCHED();
@@ -223,9 +230,10 @@ extern "C" int pcadv_bmm_tgrad(const float* x, const float* dy, float* dT, int32
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int rps = static_cast<int>((rows_per_group + splits - 1) / splits);
-  rps = (rps + 15) / 16 * 16;
+  rps = (rps + kTgChunk - 1) / kTgChunk * kTgChunk;
   splits = static_cast<int>((rows_per_group + rps - 1) / rps);
-  const size_t smem = static_cast<size_t>(32) * k * sizeof(float);
+  const size_t smem = static_cast<size_t>(2 * kTgChunk) * k * sizeof(float);
+  if (int rc = set_smem(reinterpret_cast<const void*>(bmm_tgrad_kernel), smem)) return rc;
   dim3 grid(splits, groups);
   bmm_tgrad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, dy, dT, static_cast<int>(rows_per_group),
                                                                            k, rps);
