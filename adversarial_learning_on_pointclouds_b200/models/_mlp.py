@@ -137,7 +137,7 @@ class PointMLPFunction(torch.autograd.Function):
         srcs = []
         if d_out is not None:
             d_out = d_out.contiguous().float()
-            srcs.append(d_out.reshape(d_out.shape[0], -1))
+            srcs.append(d_out.reshape(d_out.shape[0], d_out.numel() // max(d_out.shape[0], 1)))
         if d_tap is not None:
             d_tap = d_tap.contiguous().float()
             srcs.append(d_tap)

@@ -62,7 +62,7 @@ class SegFunction(torch.autograd.Function):
         B, N, _ = pts.shape
         P = B * N
         pts2 = pts.reshape(P, 3).contiguous().float()
-        cls2 = cls.reshape(B, -1).contiguous().float()
+        cls2 = cls.reshape(B, cls.shape[-1] * (cls.shape[1] if cls.dim() == 3 else 1)).contiguous().float()
         W = {n: p[n + ".weight"].reshape(p[n + ".weight"].shape[0], -1) for n in _TRUNK + _HEAD}
         b = {n: p[n + ".bias"] for n in _TRUNK + _HEAD}
 
@@ -82,7 +82,7 @@ class SegFunction(torch.autograd.Function):
                                       Layer(W["fc3"], b["fc3"], ACT_RELU),
                                       Layer(W["fc4"], b["fc4"], ACT_NONE)],
                            final_fp32=True, rows_per_group=N, group_bias=cbias, bits=hbits)
-        logits = hs[3].view(B, N, -1)
+        logits = hs[3].view(B, N, hs[3].shape[1])
         k_out = logits.shape[2]
         cols = pad64(k_out) if prec.scaled else k_out
         ctx.prec, ctx.shape, ctx.head, ctx.box = prec, (B, N), head, None
@@ -137,7 +137,7 @@ class SegFunction(torch.autograd.Function):
             ctx.box.scale2 = None
             if d_out is None:
                 d_out = torch.zeros((P, keep.shape[1]), dtype=prec.act_dtype, device=dev)
-            d2 = d_out.reshape(P, -1)
+            d2 = d_out.reshape(P, keep.shape[1])
             if scale2 is None:
                 # gradient from a consumer that does not speak the GradBox protocol: unscaled
                 d2 = d2.float().contiguous()
@@ -279,7 +279,7 @@ class SegFunction(torch.autograd.Function):
         if ctx.needs_input_grad[5]:
             wc_t = W["fc1"][:, _G1:_C1].t().contiguous()              # [16, 256]
             dcls, _, _ = ops.linear([dcb], wc_t, out_scale=inv, engine=ENGINE_SIMT)
-            dcls = dcls.view(B, 1, -1)
+            dcls = dcls.view(B, 1, dcls.shape[-1])
 
         out = []
         for n_ in PARAM_NAMES:

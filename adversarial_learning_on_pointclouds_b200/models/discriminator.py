@@ -107,7 +107,7 @@ class BaseDiscNet(nn.Module):
     def forward(self, x):
         rows, B, N, box = _rows(x)
         y = point_mlp(_prec(self), rows, [self.conv1, self.conv2, self.conv3], [_LEAKY] * 3, box=box)
-        return y.view(B, N, -1).transpose(1, 2)
+        return y.view(B, N, y.shape[-1]).transpose(1, 2)
 
 
 class ShapeDiscNet(nn.Module):
@@ -171,5 +171,5 @@ class StackDiscNet(nn.Module):
         m = point_mlp(prec, rows, [self.conv1, self.conv2, self.conv3, self.conv4], [_LEAKY] * 4,
                       reduce="channels", box=box)                                 # [B*N]
         s = point_mlp(prec, m.view(B * N, 1), [self.conv5], [_NONE])              # [B*N, S]
-        shape_logits = s.view(B, N, -1).transpose(1, 2)                           # B x S x N
+        shape_logits = s.view(B, N, s.shape[-1]).transpose(1, 2)                           # B x S x N
         return shape_logits, self.custom_activation(shape_logits)

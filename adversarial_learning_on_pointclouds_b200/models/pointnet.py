@@ -233,7 +233,7 @@ class PointNetSeg_regulization(nn.Module):
         logits = point_mlp(prec, torch.cat([x1, x2, x3, x4, x5], 1),
                            [(w1[:, :960], None), self.fc2, self.fc3, self.fc4],
                            [_RELU, _RELU, _RELU, _NONE], group=N, group_bias=cb)   # P x k
-        return logits.view(B, N, -1).transpose(1, 2), g.unsqueeze(2), trans_feat
+        return logits.view(B, N, logits.shape[-1]).transpose(1, 2), g.unsqueeze(2), trans_feat
 
 
 class PointNetDenseCls(nn.Module):

@@ -202,7 +202,8 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
                                        ":colmax" if colmax else "", ":rowmax" if rowmax else "",
                                        ":maskbits" if use_bits else (":mask" if mask is not None else ""),
                                        ":addend" if addend is not None else "")
-    _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream())
+    if rows > 0:                                   # an empty batch launches nothing
+        _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream())
     return out, ckey, rkey
 
 
@@ -259,15 +260,17 @@ def wgrad(dz, segs, *, dw=None, dbias=None, dgroup_bias=None, rows_per_group=0, 
     tag = "wgrad:%s:n%d:k%d%s%s" % ("tc" if engine == ENGINE_TC else "simt", n, ktot,
                                     ":dbias" if dbias is not None else "",
                                     ":dgroup" if dgroup_bias is not None else "")
-    _call(tag, _lib.lib().pcadv_wgrad, C.byref(a), _stream())
+    if rows > 0:
+        _call(tag, _lib.lib().pcadv_wgrad, C.byref(a), _stream())
 
 
 def max_finalize(key, act=ACT_NONE, slope=0.0, want_idx=True):
     """Unpack packed max keys -> (val fp32, idx int32) with the shape of ``key``."""
     val = torch.empty(key.shape, dtype=torch.float32, device=key.device)
     idx = torch.empty(key.shape, dtype=torch.int32, device=key.device) if want_idx else None
-    _call("max_finalize", _lib.lib().pcadv_max_finalize, _ptr(key), key.numel(), act, float(slope),
-          _ptr(val), _ptr(idx), _stream())
+    if key.numel() > 0:
+        _call("max_finalize", _lib.lib().pcadv_max_finalize, _ptr(key), key.numel(), act, float(slope),
+              _ptr(val), _ptr(idx), _stream())
     return val, idx
 
 
@@ -283,6 +286,8 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
     sparse contribution in place, through the previous layer's activation mask."""
     a = _lib.MaxBwdArgs()
     groups, n = dg.shape
+    if groups == 0:
+        return
     a.groups, a.n, a.k = groups, n, w.shape[1]
     a.act, a.slope = act, float(slope)
     a.rows_per_group = int(rows_per_group)
@@ -313,6 +318,8 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
 def rowmax_bwd(dy, val, idx, n, *, act=ACT_NONE, slope=0.0, scale=None, out_dtype=torch.float32):
     rows = dy.numel()
     dz = torch.empty((rows, n), dtype=out_dtype, device=dy.device)
+    if rows == 0:
+        return dz
     _call("rowmax_bwd:n%d" % n, _lib.lib().pcadv_rowmax_bwd, _f32(dy), _f32(val), _ptr(idx), rows, n,
           act, float(slope), _f32(scale) if scale is not None else None, _ptr(dz), n, _DT[out_dtype],
           _stream())
@@ -327,6 +334,8 @@ def rowmax_dgrad(dy, val, idx, w, yprev, *, act=ACT_NONE, slope=0.0, scale=None,
     wp, ldw, wdt = _mat(w)
     yp, ldy, ydt = _mat(yprev)
     dz = torch.empty((rows, k), dtype=out_dtype, device=yprev.device)
+    if rows == 0:
+        return dz
     _call("rowmax_dgrad:k%d" % k, _lib.lib().pcadv_rowmax_dgrad, _f32(dy), _f32(val), _ptr(idx), rows, k,
           act, float(slope), _f32(scale) if scale is not None else None, wp, ldw, wdt, yp, ldy, ydt,
           prev_act, float(prev_slope), _ptr(dz), k, _DT[out_dtype], _stream())
@@ -337,6 +346,8 @@ def rowmax_wgrad(dy, val, idx, yprev, n, *, act=ACT_NONE, slope=0.0, dw=None, db
     """fp32 (dw [n, k], dbias [n]) of a layer followed by a max over channels, accumulated
     into: see ``pcadv_rowmax_wgrad``."""
     rows, k = yprev.shape
+    if rows == 0:
+        return
     yp, ldy, ydt = _mat(yprev)
     dwp, ld_dw = (C.c_void_p(0), 0)
     if dw is not None:
@@ -356,7 +367,12 @@ def amax_scale(xs, target=256.0):
     dev = xs[0].device
     ws = torch.zeros(1, dtype=torch.int32, device=dev)
     s2 = torch.empty(2, dtype=torch.float32, device=dev)
+    if all(x.numel() == 0 for x in xs):
+        s2.fill_(1.0)
+        return s2
     for x in xs:
+        if x.numel() == 0:
+            continue
         p, ld, dt = _mat(x)
         if dt != F32:
             raise ValueError("amax_scale expects fp32")
@@ -371,6 +387,8 @@ def convert(src, out_dtype, cols_pad=None, scale=None, mask=None, mask_act=ACT_N
     rows, cols = src.shape
     cols_pad = int(cols_pad or cols)
     dst = torch.empty((rows, cols_pad), dtype=out_dtype, device=src.device)
+    if rows == 0:
+        return dst
     mp, mld, mdt = _mat(mask) if mask is not None else (C.c_void_p(0), 0, F32)
     _call("convert:c%d" % cols_pad, _lib.lib().pcadv_convert, p, dt, ld, rows, cols, _ptr(dst),
           _DT[out_dtype], cols_pad, cols_pad, _f32(scale) if scale is not None else None, mp, mld, mdt,
@@ -390,6 +408,8 @@ def convert_cm(x_bcn, out_dtype, cols_pad=None, scale=None):
     B, Cn, N = x_bcn.shape
     cols_pad = int(cols_pad or Cn)
     dst = torch.empty((B * N, cols_pad), dtype=out_dtype, device=x_bcn.device)
+    if B * N == 0:
+        return dst
     _call("convert_cm:c%d" % cols_pad, _lib.lib().pcadv_convert_cm, _ptr(x_bcn), x_bcn.stride(0),
           x_bcn.stride(1), B, N, Cn, _ptr(dst), _DT[out_dtype], cols_pad, cols_pad,
           _f32(scale) if scale is not None else None, _stream())
@@ -421,6 +441,8 @@ def softmax_head(logits, mode, *, labels=None, out_dtype=torch.float32, cols=Non
         a.dz, a.ld_dz, a.dz_dtype, a.dz_cols = _ptr(dz), cols, _DT[out_dtype], cols
     a.dz_gain = float(dz_gain)
     a.loss_sum = _f32(loss_sum) if loss_sum is not None else None
+    if rows == 0:
+        return probs, dz
     _call("softmax_head:%s" % ("ce" if mode == _lib.HEAD_CE else "lsm"), _lib.lib().pcadv_softmax_head,
           C.byref(a), _stream())
     return probs, dz
@@ -434,6 +456,8 @@ def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None)
     rows = lp.shape[0]
     cols = int(cols or n)
     dz = torch.empty((rows, cols), dtype=out_dtype, device=lp.device)
+    if rows == 0:
+        return dz
     _call("logsoftmax_bwd", _lib.lib().pcadv_logsoftmax_bwd, lpp, lpd, ld_lp, dyp, dyd, ld_dy, rows, int(n),
           _f32(scale) if scale is not None else None, _ptr(dz), _DT[out_dtype], cols, cols, _stream())
     return dz
@@ -449,6 +473,8 @@ def bmm(x, trans, transpose_t=False):
     """y[b] = x[b] @ T[b] (or @ T[b]^T) for x [B, N, k], T [B, k, k] fp32: see ``pcadv_bmm``."""
     B, N, k = x.shape
     y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
     _call("bmm:k%d" % k, _lib.lib().pcadv_bmm, _f32c(x), _f32c(trans), _f32c(y), B, N, k,
           1 if transpose_t else 0, _stream())
     return y
@@ -458,6 +484,8 @@ def bmm_tgrad(x, dy):
     """dT[b] = x[b]^T @ dy[b] for x, dy [B, N, k] fp32: see ``pcadv_bmm_tgrad``."""
     B, N, k = x.shape
     dT = torch.zeros((B, k, k), dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return dT
     _call("bmm_tgrad:k%d" % k, _lib.lib().pcadv_bmm_tgrad, _f32c(x), _f32c(dy), _f32c(dT), B, N, k, _stream())
     return dT
 

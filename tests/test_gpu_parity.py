@@ -553,6 +553,28 @@ def test_tnet_bmm_and_regulariser_kernels(B, N, k):
     assert rel_err(T.grad, Td.grad) < 2e-5
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_empty_batch_and_single_point(mode):
+    """Edge shapes: an empty batch launches nothing and yields empty outputs and zero gradients;
+    clouds of one point work (the max over points is that point)."""
+    g = build_seg(1, 2).to(DEV)
+    d = init_net(M.PointwiseDiscNet(64, 50), "cpu", "xavier").to(DEV)
+    g.precision = d.precision = Precision(mode)
+    pts = torch.zeros(0, 64, 3, device=DEV)
+    cls = torch.zeros(0, 1, 16, device=DEV)
+    pred, glob = g(pts, cls)
+    assert tuple(pred.shape) == (0, 50, 64) and tuple(glob.shape) == (0, 2048, 1)
+    out = d(F.log_softmax(pred, 1))
+    assert tuple(out.shape) == (0, 64)
+    (pred.sum() + out.sum()).backward()
+    assert all(p.grad is None or p.grad.abs().sum().item() == 0 for p in g.parameters())
+    pts, _, seg, cls = inputs(2, 1, 5)
+    pred, glob = g(pts.to(DEV), cls.to(DEV))
+    gp = steps.leaf_params({k: v.detach().cpu() for k, v in g.state_dict().items()})
+    o_pred, o_glob = PO.pointnet_seg_forward(gp, pts, cls)
+    assert rel_err(pred, o_pred) < (1e-5 if mode == "fp32" else 2e-3)
+
+
 def test_launch_counter_counts():
     before = pkg._lib.launch_count()
     x = _rand((256, 64), 1)
