@@ -46,7 +46,7 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while running."""
+    """Samples nvidia-smi clocks / throttle reasons back to back (one query is ~30-50 ms) while running."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([v.strip() for v in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         sm, reasons, smax = [], set(), None
