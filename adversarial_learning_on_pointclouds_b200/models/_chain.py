@@ -12,6 +12,35 @@ from .. import ops
 from ..ops import ACT_NONE, ENGINE_TC
 
 
+class ZeroPool:
+    """One zero-filled fp32 buffer per backward pass, carved into the dW / dbias accumulators the
+    wgrad kernels add into: one fill kernel instead of one per tensor.  Slices start on 16-byte
+    boundaries (the vector RED path of tc_wgrad wants that)."""
+
+    def __init__(self, numel, device):
+        self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.off + n > self.buf.numel():
+            return torch.zeros(shape, dtype=torch.float32, device=self.buf.device)
+        t = self.buf[self.off:self.off + n].view(shape)
+        self.off += (n + 3) // 4 * 4
+        return t
+
+    @staticmethod
+    def size_for(layers_nk):
+        """Elements needed for [(n_pad, k_total)] layers (dW + dbias each), with alignment slack."""
+        return sum(n * k + n + 8 for n, k in layers_nk)
+
+
+def _zeros(pool, shape, device):
+    return pool.take(*shape) if pool is not None else torch.zeros(shape, dtype=torch.float32, device=device)
+
+
 class Layer:
     """One pointwise layer: y = act(x W^T + b)."""
 
@@ -24,9 +53,45 @@ class Layer:
         self.slope = slope
 
 
+# ---- per-step cache of the engine copies of the weights ------------------------------------------
+# Inside ``with weight_cache():`` (the trainer's step functions) a parameter is converted /
+# transposed / K-concatenated once and reused by every pass of the step that needs the same copy
+# (G runs two forward and two backward passes per step, D three and two and a half).  Keys carry
+# the tensor's storage, view geometry and autograd version counter, so an in-place optimizer update
+# inside the scope invalidates the entry; the cache dies with the scope, so nothing captured into a
+# CUDA graph is ever looked up from eager code later.
+_WCACHE = None
+
+
+class weight_cache:
+    def __enter__(self):
+        global _WCACHE
+        self._prev, _WCACHE = _WCACHE, ({} if _WCACHE is None else _WCACHE)
+        return self
+
+    def __exit__(self, *exc):
+        global _WCACHE
+        _WCACHE = self._prev
+
+
+def _wkey(kind, prec, tensors, extra):
+    return (kind, prec.name, tuple((t.data_ptr(), tuple(t.shape), t.stride(), t._version) for t in tensors),
+            tuple(extra))
+
+
 def compute_weight(prec, w32, k_list, n):
     """The copy of a weight matrix the engine multiplies with: a 16-bit copy when
     the tensor-core engine can take the shape, else the fp32 master."""
+    if _WCACHE is not None:
+        key = _wkey("cw", prec, [w32], list(k_list) + [n])
+        hit = _WCACHE.get(key)
+        if hit is None:
+            hit = _WCACHE[key] = _compute_weight(prec, w32, k_list, n)
+        return hit
+    return _compute_weight(prec, w32, k_list, n)
+
+
+def _compute_weight(prec, w32, k_list, n):
     ktot = sum(k_list)
     if ktot != w32.shape[1]:                     # input carries zero-padded columns (K = 50 -> 64)
         w32 = pad_cols(w32, ktot)
@@ -93,6 +158,16 @@ def dgrad_weight(prec, blocks, n_out, widths):
     ``blocks`` = list of [Cout_i, n_out] forward-weight slices (fp32), ``widths`` the
     column counts of the dz matrices they multiply (>= Cout_i when dz carries
     zero padding); the result is [n_out, sum(widths)] in the compute dtype."""
+    if _WCACHE is not None:
+        key = _wkey("dg", prec, blocks, [n_out] + list(widths))
+        hit = _WCACHE.get(key)
+        if hit is None:
+            hit = _WCACHE[key] = _dgrad_weight(prec, blocks, n_out, widths)
+        return hit
+    return _dgrad_weight(prec, blocks, n_out, widths)
+
+
+def _dgrad_weight(prec, blocks, n_out, widths):
     parts = []
     for wb, width in zip(blocks, widths):
         parts.append(pad_cols(wb.t(), width))
@@ -103,7 +178,7 @@ def dgrad_weight(prec, blocks, n_out, widths):
     return wt
 
 
-def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0):
+def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0, pool=None):
     """fp32 (dw, db) of one layer from its dz and input segments.  ``dz`` may carry
     zero-padded columns beyond w_shape[0]."""
     if not (need_w or need_b):
@@ -111,8 +186,8 @@ def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0)
     n_pad = dz.shape[1]
     dev = dz.device
     ktot = sum(s.shape[1] for s in x_segs)
-    dw = torch.zeros((n_pad, ktot + extra_cols), dtype=torch.float32, device=dev) if need_w else None
-    db = torch.zeros((n_pad,), dtype=torch.float32, device=dev) if need_b else None
+    dw = _zeros(pool, (n_pad, ktot + extra_cols), dev) if need_w else None
+    db = _zeros(pool, (n_pad,), dev) if need_b else None
     inv = scale2[1:2] if scale2 is not None else None
     ops.wgrad(dz, x_segs if need_w else [], dw=dw[:, :ktot] if need_w else None, dbias=db, scale=inv,
               engine=prec.engine)
@@ -121,7 +196,7 @@ def layer_wgrad(prec, dz, x_segs, w_shape, need_w, need_b, scale2, extra_cols=0)
 
 
 def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, scale2, addends=None,
-                   dx_packed=False, bits=None):
+                   dx_packed=False, bits=None, pool=None):
     """Backward through a chain.  ``dz_last``: dz of the last layer ([rows, pad(n)]).
     ``need_w[i]`` / ``need_b[i]``: which parameter gradients to form (frozen
     discriminators skip wgrad, utils/trainer.py:885-886).  Returns
@@ -135,7 +210,7 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
     for i in range(len(layers) - 1, -1, -1):
         L = layers[i]
         xin = x_segs if i == 0 else [ys[i - 1]]
-        grads[i] = layer_wgrad(prec, dz, xin, L.w.shape, need_w[i], need_b[i], scale2)
+        grads[i] = layer_wgrad(prec, dz, xin, L.w.shape, need_w[i], need_b[i], scale2, pool=pool)
         if i == 0:
             break
         P = layers[i - 1]

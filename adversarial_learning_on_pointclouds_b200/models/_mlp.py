@@ -9,8 +9,8 @@ import torch
 
 from .. import ops
 from ..ops import ACT_NONE, ENGINE_SIMT
-from ._chain import (Layer, chain_forward, chain_backward, compute_weight, prepare_dz, layer_wgrad,
-                     dgrad_weight)
+from ._chain import (Layer, ZeroPool, chain_forward, chain_backward, compute_weight, prepare_dz,
+                     layer_wgrad, dgrad_weight)
 
 
 class MLPSpec:
@@ -147,6 +147,10 @@ class PointMLPFunction(torch.autograd.Function):
         S = scale2[0:1] if prec.scaled else None
         inv = scale2[1:2] if prec.scaled else None
 
+        pool = None
+        if any(need_w) or any(need_b):
+            pad = lambda n: (n + 63) // 64 * 64
+            pool = ZeroPool(ZeroPool.size_for([(pad(L.w.shape[0]), pad(L.w.shape[1])) for L in layers]), dev)
         addends = {}
         if d_tap is not None:
             addends[spec.tap] = d_tap * S if prec.scaled else d_tap
@@ -169,8 +173,8 @@ class PointMLPFunction(torch.autograd.Function):
                 n, k_true = L.w.shape
                 dy = d_out.reshape(-1)
                 if need_w[-1] or need_b[-1]:
-                    dw = torch.zeros((n, src.shape[1]), dtype=torch.float32, device=dev) if need_w[-1] else None
-                    db = torch.zeros((n,), dtype=torch.float32, device=dev) if need_b[-1] else None
+                    dw = pool.take(n, src.shape[1]) if need_w[-1] else None
+                    db = pool.take(n) if need_b[-1] else None
                     ops.rowmax_wgrad(dy, red_val, red_idx, src, n, act=L.act, slope=L.slope, dw=dw, dbias=db)
                     grads[-1] = (dw[:, :k_true] if dw is not None else None, db)
                 P_ = body[-1]
@@ -221,13 +225,14 @@ class PointMLPFunction(torch.autograd.Function):
                                mask_slope=P_.slope)
             g2, dx, dz0 = chain_backward(prec, dz_t, [x_in], ys[:t + 1], body[:t + 1],
                                          need_w[:t + 1], need_b[:t + 1], need_x, scale2,
-                                         dx_packed=ctx.packed_in, bits=ybits[:t + 1])
+                                         dx_packed=ctx.packed_in, bits=ybits[:t + 1], pool=pool)
             for i, gr in enumerate(g2):
                 grads[i] = gr
         elif body and dz_last is not None:
             g2, dx, dz0 = chain_backward(prec, dz_last, [x_in], ys[:len(body)], body,
                                          need_w[:len(body)], need_b[:len(body)], need_x, scale2,
-                                         addends=addends, dx_packed=ctx.packed_in, bits=ybits[:len(body)])
+                                         addends=addends, dx_packed=ctx.packed_in, bits=ybits[:len(body)],
+                                         pool=pool)
             for i, gr in enumerate(g2):
                 grads[i] = gr
         dgb = None

@@ -15,7 +15,7 @@ import torch
 
 from .. import ops
 from ..ops import ACT_NONE, ACT_RELU, ENGINE_SIMT, HEAD_CE, HEAD_LSM
-from ._chain import (Layer, chain_forward, compute_weight, dgrad_weight, layer_wgrad, prepare_dz)
+from ._chain import (Layer, ZeroPool, chain_forward, compute_weight, dgrad_weight, layer_wgrad, prepare_dz)
 
 _TRUNK = ("conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
 _HEAD = ("fc1", "fc2", "fc3", "fc4")
@@ -206,12 +206,16 @@ class SegFunction(torch.autograd.Function):
             inv = scale2[1:2] if prec.scaled else None
             dz = prepare_dz(prec, dl, scale2)
 
+        # every dW / dbias accumulator of this pass comes out of one zero-filled buffer
+        pool = ZeroPool(ZeroPool.size_for([(64, 128), (128, 256), (256, 256), (256, _C1), (B, 256),
+                                           (2048, 512), (512, 128), (128, 128), (128, 128), (128, 64),
+                                           (64, 64)]), dev)
         # ---- head: fc4, fc3, fc2 ---------------------------------------------------
         head = (("fc4", ACT_NONE), ("fc3", ACT_RELU), ("fc2", ACT_RELU))
         for li, (name, _) in enumerate(head):
             xin = hs[2 - li]
             dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
-                                 need[name + ".bias"], scale2)
+                                 need[name + ".bias"], scale2, pool=pool)
             grads[name + ".weight"], grads[name + ".bias"] = dw, db
             wt = dgrad_weight(prec, [W[name]], W[name].shape[1], [dz.shape[1]])
             dz, _, _ = ops.linear([dz], wt, mask=xin, mask_act=ACT_RELU, out_dtype=prec.act_dtype,
@@ -220,9 +224,9 @@ class SegFunction(torch.autograd.Function):
 
         # ---- fc1: per-point part (x1..x5) and per-cloud part (g, cls, bias) -----------
         need_w1, need_b1 = need["fc1.weight"], need["fc1.bias"]
-        dw1 = torch.zeros((256, _C1), dtype=torch.float32, device=dev) if need_w1 else None
-        db1 = torch.zeros((256,), dtype=torch.float32, device=dev) if need_b1 else None
-        dcb = torch.zeros((B, 256), dtype=torch.float32, device=dev)   # d(cbias), scaled
+        dw1 = pool.take(256, _C1) if need_w1 else None
+        db1 = pool.take(256) if need_b1 else None
+        dcb = pool.take(B, 256)                                        # d(cbias), scaled
         ops.wgrad(dz_fc1, xs if need_w1 else [], dw=dw1[:, :_G0] if need_w1 else None,
                   dgroup_bias=dcb, rows_per_group=N, scale=inv, engine=prec.engine)
         if need_w1 or need_b1:
@@ -235,8 +239,8 @@ class SegFunction(torch.autograd.Function):
         dg, _, _ = ops.linear([dcb], wg_t, engine=ENGINE_SIMT)        # [B, 2048], scaled
         if dg_ext is not None:
             dg = dg + (dg_ext.float() * scale2[0] if prec.scaled else dg_ext.float())
-        dw6 = torch.zeros((2048, 512), dtype=torch.float32, device=dev) if need["conv6.weight"] else None
-        db6 = torch.zeros((2048,), dtype=torch.float32, device=dev) if need["conv6.bias"] else None
+        dw6 = pool.take(2048, 512) if need["conv6.weight"] else None
+        db6 = pool.take(2048) if need["conv6.bias"] else None
         # ---- trunk: dz_k = relu'(x_k) * ([dz_{k+1} | dz_fc1] @ [W_{k+1}; fc1.W[:, slice_k]]) --
         s5 = _SLICES[4]
         wt = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512, [256])
@@ -259,7 +263,7 @@ class SegFunction(torch.autograd.Function):
             name = _TRUNK[li]
             xin = xs[li - 1]
             dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
-                                 need[name + ".bias"], scale2)
+                                 need[name + ".bias"], scale2, pool=pool)
             grads[name + ".weight"], grads[name + ".bias"] = dw, db
             sl = _SLICES[li - 1]
             wt = dgrad_weight(prec, [W[name], W["fc1"][:, sl[0]:sl[1]]], W[name].shape[1],
@@ -267,7 +271,7 @@ class SegFunction(torch.autograd.Function):
             dz, _, _ = ops.linear([dz, dz_fc1], wt, mask=xin, mask_act=ACT_RELU,
                                   out_dtype=prec.act_dtype, engine=prec.engine, mask_bits=xbits[li - 1])
         dw, db = layer_wgrad(prec, dz, [pts2], W["conv1"].shape, need["conv1.weight"],
-                             need["conv1.bias"], scale2)
+                             need["conv1.bias"], scale2, pool=pool)
         grads["conv1.weight"], grads["conv1.bias"] = dw, db
 
         dpts = None

@@ -11,6 +11,7 @@ four times per iteration, :900, :925, :948, :963).
 import torch
 import torch.nn.functional as F
 
+from .models._chain import weight_cache
 from .utils.utils import make_D_label
 from .utils.image_pool import ImagePool
 
@@ -24,9 +25,22 @@ def _device_label(like, value, random):
     return torch.empty_like(like).uniform_(lo, hi)
 
 
-def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
-                         batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
-                         device_labels=False, label_fn=None):
+def adversarial_seg_step(*a, **kw):
+    """One iteration of run_training_seg (utils/trainer.py:873-966); see ``_adversarial_seg_step``.
+    The engine copies of the weights are shared by the passes of the step (``weight_cache``)."""
+    with weight_cache():
+        return _adversarial_seg_step(*a, **kw)
+
+
+def adversarial_seg_step_fused(*a, **kw):
+    """The same iteration through the fused loss heads; see ``_adversarial_seg_step_fused``."""
+    with weight_cache():
+        return _adversarial_seg_step_fused(*a, **kw)
+
+
+def _adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
+                          batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
+                          device_labels=False, label_fn=None):
     """One iteration of run_training_seg (utils/trainer.py:873-966).
 
     batch_gt = (pts B x N x 3, cls B x 1 x 16, seg B x N), batch_nogt = (pts, cls),
@@ -77,9 +91,9 @@ def adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimize
     return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
 
 
-def adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
-                               batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
-                               device_labels=False, label_fn=None):
+def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
+                                batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
+                                device_labels=False, label_fn=None):
     """The same iteration (utils/trainer.py:873-966) through the generator's fused loss heads
     (SURVEY.md 8f rank 1): ``CrossEntropyLoss`` + ``softmax`` of the labelled pass and
     ``log_softmax`` of the unlabelled pass are one kernel each over the logits, and the
