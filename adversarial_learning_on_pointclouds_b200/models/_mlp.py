@@ -8,6 +8,7 @@ precision mode's storage dtype and gradients carry a dynamic power-of-two scale.
 import torch
 
 from .. import ops
+from . import _chain
 from ..ops import ACT_NONE, ENGINE_SIMT
 from ._chain import (Layer, ZeroPool, chain_forward, chain_backward, compute_weight, prepare_dz,
                      layer_wgrad, dgrad_weight)
@@ -47,6 +48,26 @@ class PointMLPFunction(torch.autograd.Function):
             raise RuntimeError("libpcadv layers need CUDA tensors; there is no CPU path")
         nl = len(spec.acts)
         layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
+        # Inside a step scope (``weight_cache``) a forward over the very same input and weights is
+        # not repeated: the trainer evaluates D(log_softmax(pred_nogt)) in the G phase and again on
+        # the detached tensor in the D phase (utils/trainer.py:916, :951-953).
+        cache = _chain._WCACHE if gb is None and spec.tap is None else None
+        fkey = None
+        if cache is not None:
+            ident = lambda t: None if t is None else (t.data_ptr(), tuple(t.shape), t.stride(), t._version, t.dtype)
+            fkey = ("fwd", prec.name, tuple(spec.acts), spec.reduce, spec.group, ident(x),
+                    tuple(ident(p_) for p_ in params))
+            hit = cache.get(fkey)
+            if hit is not None:
+                x_in, ys, ybits, red_val, red_idx, ctx.bcn, ctx.packed_in, out = hit
+                ctx.prec, ctx.spec = prec, spec
+                ctx.n_ys = len(ys)
+                ctx.has_red = red_val is not None
+                ctx.has_gb = False
+                ctx.bit_slots = [i for i, t in enumerate(ybits) if t is not None]
+                ctx.save_for_backward(*([x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) +
+                                        list(params) + [ybits[i] for i in ctx.bit_slots]))
+                return out.detach()
         ctx.bcn = None
         ctx.packed_in = False
         x_in = None
@@ -105,6 +126,9 @@ class PointMLPFunction(torch.autograd.Function):
         saved = [x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) + list(params) + \
             [ybits[i] for i in ctx.bit_slots]
         ctx.save_for_backward(*saved)
+        if fkey is not None:
+            cache[fkey] = (x_in, ys, ybits, red_val, red_idx, ctx.bcn, ctx.packed_in, out)
+            return out.detach()
         if tap is not None:
             return out, tap
         return out
