@@ -314,6 +314,51 @@ __global__ void __launch_bounds__(256) group_colsum_kernel(const void* dz, int d
   }
 }
 
+// 16-bit dz with 16-byte aligned rows: thread = (8-column group, row lane), 16-byte loads, four
+// rows in flight per thread
+__global__ void __launch_bounds__(256) group_colsum16_kernel(const uint16_t* __restrict__ dz, int bf16,
+                                                            int64_t ld, int n, int64_t rows_per_group,
+                                                            float* out) {
+  __shared__ float red[32][65];
+  const int cgi = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cgi * 8;
+  const int64_t g = blockIdx.y;
+  const uint16_t* base = dz + g * rows_per_group * ld + c0;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < n) {
+    for (int64_t r = rl; r < rows_per_group; r += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = r + 32 * u < rows_per_group ? __ldg(reinterpret_cast<const uint4*>(base + (r + 32 * u) * ld))
+                                           : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f;
+          if (bf16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+          else f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+          acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][cgi * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float sum = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) sum += red[i][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < n) out[g * n + c] += sum;
+  }
+}
+
 // =====================================================================================
 // First layer (K <= 4, e.g. Conv1d(3, 64, 1) at models/pointnet.py:115, :291): HBM-bound.
 // One thread = one point x 8 output channels: the point's xyz is a broadcast load, the
@@ -590,7 +635,11 @@ int launch_group_colsum(const void* dz, int dz_dtype, int64_t ld, int64_t rows, 
   PCADV_CHECK_ARG(rows % rows_per_group == 0, "rows (%lld) not a multiple of rows_per_group (%lld)",
                   (long long)rows, (long long)rows_per_group);
   dim3 grid((n + 63) / 64, static_cast<unsigned>(rows / rows_per_group));
-  group_colsum_kernel<<<grid, 256, 0, s>>>(dz, dz_dtype, ld, n, rows_per_group, out);
+  if (dz_dtype != PCADV_F32 && n % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0)
+    group_colsum16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(dz), dz_dtype == PCADV_BF16 ? 1 : 0,
+                                               ld, n, rows_per_group, out);
+  else
+    group_colsum_kernel<<<grid, 256, 0, s>>>(dz, dz_dtype, ld, n, rows_per_group, out);
   PCADV_LAUNCHED();
   return 0;
 }

@@ -331,9 +331,15 @@ tc_wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p) {
 int launch_group_colsum(const void* dz, int dz_dtype, int64_t ld, int64_t rows, int n,
                         int64_t rows_per_group, float* out, cudaStream_t s);
 
+int tc_wgrad_pair(const pcadv_wgrad_args& a, cudaStream_t s);   // tc_wgrad2.cu
+
 int tc_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
   using namespace tc;
   const int dt = a.dz_dtype;
+  if (dt == PCADV_F16 || dt == PCADV_BF16) {
+    const int rc = tc_wgrad_pair(a, s);                  // CTA-pair kernel for 256 x wide-K layers
+    if (rc >= 0) return rc;
+  }
   PCADV_CHECK_ARG(dt == PCADV_F16 || dt == PCADV_BF16, "tc_wgrad: dz must be fp16 / bf16");
   PCADV_CHECK_ARG(a.dw != nullptr && a.num_seg >= 1, "tc_wgrad: dw and segments required");
   PCADV_CHECK_ARG(a.n % 64 == 0 && tma_compatible(a.dz, dt, a.ld_dz),

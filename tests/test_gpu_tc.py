@@ -150,3 +150,22 @@ def test_caller_buffers_are_not_overrun(rows):
     lp, _ = ops.softmax_head(logits, ops.HEAD_LSM, out_dtype=dtype, cols=64)
     assert rel_err(lp[:, :50], torch.log_softmax(logits.double(), 1)) < 2e-3
     assert lp[:, 50:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,ks,rpg", [(4096, [64, 128, 128, 128, 512], 1024), (19984, [512], 0),
+                                         (70001, [64, 128, 128, 128, 512], 0), (8192, [512, 512], 2048)])
+def test_tc_wgrad_cta_pair(dtype, rows, ks, rpg):
+    """The cta_group::2 weight-gradient kernel (dz of 256 channels, K-concat of >= 512): dW and the
+    fused per-cloud column sums against fp64."""
+    n = 256
+    dz = _rand((rows, n), 51, dtype)
+    segs = [_rand((rows, k), 52 + i, dtype) for i, k in enumerate(ks)]
+    dw = torch.zeros((n, sum(ks)), device=DEV)
+    dgb = torch.zeros((rows // rpg, n), device=DEV) if rpg else None
+    sc = torch.tensor([0.25], device=DEV)
+    ops.wgrad(dz, segs, dw=dw, dgroup_bias=dgb, rows_per_group=rpg, scale=sc, engine=ENGINE_TC)
+    ref = 0.25 * dz.double().t() @ torch.cat(segs, 1).double()
+    assert rel_err(dw, ref) < 1e-5
+    if rpg:
+        assert rel_err(dgb, dz.double().view(rows // rpg, rpg, n).sum(1)) < 1e-6

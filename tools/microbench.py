@@ -85,6 +85,13 @@ def cases(P, N):
                    2.0 * P * n * sum(ks))
 
     wg("wg_fc1", 256, [64, 128, 128, 128, 512], dbias=False)
+    dzg = r16((P, 256))
+    segg = [r16((P, k)) for k in [64, 128, 128, 128, 512]]
+    dwg = torch.zeros((256, 3024), device=DEV)
+    dcb = torch.zeros((B, 256), device=DEV)
+    s2 = torch.ones(2, device=DEV)
+    c["wg_fc1_g"] = (lambda: ops.wgrad(dzg, segg, dw=dwg[:, :960], dgroup_bias=dcb, rows_per_group=N,
+                                       scale=s2[1:2], engine=ENGINE_TC), P * 2 * (256 + 960), 2.0 * P * 256 * 960)
     wg("wg_conv5", 512, [128])
     wg("wg_fc2", 256, [256])
     wg("wg_conv3", 128, [128])
