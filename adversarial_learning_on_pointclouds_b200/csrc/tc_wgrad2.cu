@@ -10,10 +10,14 @@
 //
 // Protocol (per stage): both producers wait for their own `empty` barrier, the leader's producer
 // posts arrive.expect_tx for BOTH CTAs' bytes on its `full` barrier, both issue TMA loads that
-// complete_tx on the leader's `full` (cta_group::2 form); the leader's MMA thread waits `full`
-// (the peer learns that its boxes have landed by a remote arrive on its `landed`, used by the column
-// sums; sent by an epilogue thread), issues the MMAs and commits with a multicast arrive to both
-// CTAs' `empty`.
+// complete_tx on the leader's `full` (cta_group::2 form); the leader's MMA thread waits `full`,
+// issues the MMAs and commits with a multicast arrive to both CTAs' `empty`.
+//
+// The per-cloud column sums of dz (the gradient of fc1's per-cloud bias) are NOT taken from the
+// boxes in flight as in the single-CTA kernel: the peer CTA would have to be told that its boxes
+// have landed (a cross-CTA arrive per stage) before its sum warps may run and release the stage;
+// measured, that hand-off costs 0.28 ms on fc1 against 0.1 ms for a separate pass over dz
+// (group_colsum16_kernel), so the host launches that pass instead.
 #include <stdlib.h>
 #include "tc_pipeline.cuh"
 
@@ -29,8 +33,7 @@ constexpr int kW2SmemMax = 232448;
 
 struct W2Tail {
   uint64_t full[kW2Stages];       // leader only: 1 arrival + both CTAs' bytes
-  uint64_t empty[kW2Stages];      // per CTA: multicast MMA commit (+ 4 epilogue warps with column sums)
-  uint64_t landed[kW2Stages];     // peer only: the leader's "your boxes are in shared memory"
+  uint64_t empty[kW2Stages];      // per CTA: the leader's multicast MMA commit
   uint64_t tmem_full;
   uint32_t tmem_base;
 };
@@ -49,8 +52,6 @@ struct W2Params {
   float* dw;
   int64_t ld_dw;
   int vec_red;
-  float* dgroup_bias;             // [rows / rows_per_group, 256] or NULL (NOT scaled)
-  int64_t rows_per_group;
   const float* scale;
 };
 
@@ -67,9 +68,6 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of the 2-CTA form: lands in the executing CTA's shared memory, signals `mbar_cluster`
 // (a shared::cluster address, here the leader's full barrier)
@@ -112,17 +110,6 @@ __device__ __forceinline__ void red_add_v4_w2(float* addr, float a, float b, flo
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
-template <bool kBf16>
-__device__ __forceinline__ void add_pair_f32_w2(uint32_t packed, float2& acc) {
-  if (kBf16) {
-    asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.bf16 %0, lo, %0;\nadd.rn.f32.bf16 %1, hi, %1;\n}"
-        : "+f"(acc.x), "+f"(acc.y) : "r"(packed));
-  } else {
-    asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.f16 %0, lo, %0;\nadd.rn.f32.f16 %1, hi, %1;\n}"
-        : "+f"(acc.x), "+f"(acc.y) : "r"(packed));
-  }
-}
-
 // tile box j (0..7) of the pair's N tile -> which CTA holds it and where: the two N = 256 MMAs read
 // local boxes {0, 1} and {2, 3} of both CTAs, CTA 0's columns first
 __device__ __forceinline__ int tile_box_of(int rank, int local) { return (local >> 1) * 4 + rank * 2 + (local & 1); }
@@ -137,7 +124,6 @@ tc_wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const W2Params p) 
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const bool sums = p.dgroup_bias != nullptr;
   // one work item per pair (host guarantees tiles_n * splits <= pairs)
   const int num_work = p.tiles_n * p.splits;
   const bool has_work = pair < num_work;
@@ -152,8 +138,7 @@ tc_wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const W2Params p) 
     tma_prefetch_desc(&maps.w);
     for (int i = 0; i < kW2Stages; ++i) {
       mbar_init(&st->full[i], 1);
-      mbar_init(&st->empty[i], sums ? 5 : 1);
-      mbar_init(&st->landed[i], 1);
+      mbar_init(&st->empty[i], 1);
     }
     mbar_init(&st->tmem_full, 1);
     fence_barrier_init();
@@ -221,77 +206,10 @@ tc_wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const W2Params p) 
       umma_commit_pair(&st->tmem_full);
     }
   } else {
-    // ---------------- epilogue warps (both CTAs): column sums in flight, then the tile ----------------
+    // ---------------- epilogue warps (both CTAs): this CTA's 128 x 512 half of the tile ----------------
     const int quarter = warp & 3;
     const int lane_row = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;                  // 0..127
     const float sc = p.scale ? *p.scale : 1.f;
-    if (sums) {
-      // per-cloud column sums of this CTA's 128 dz channels from the boxes in flight: thread =
-      // (8-channel group, 8-row group), one 16-byte shared load per row, eight independent fp32
-      // accumulators; a warp holds two row groups of all 16 channel groups
-      const int cg = et & 15, rg = et >> 4;
-      const uint32_t box_off = static_cast<uint32_t>(cg >> 3) * kW2BoxBytes;
-      const uint32_t chunk = static_cast<uint32_t>(cg & 7);
-      const int ch = static_cast<int>(rank) * 128 + cg * 8;
-      float gsum[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) gsum[e] = 0.f;
-      int64_t cur_g = -1;
-      auto flush = [&]() {
-        if (cur_g >= 0 && (lane & 16) == 0) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) atomicAdd(p.dgroup_bias + cur_g * 256 + ch + e, gsum[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gsum[e] = 0.f;
-      };
-      uint32_t phase = 0;
-      int stage = 0;
-      for (int it = 0; it < nstage_iters; ++it) {
-        if (leader) {
-          mbar_wait_backoff(&st->full[stage], phase);
-          // tell the peer's column-sum warps that the stage has landed.  Not from the MMA thread:
-          // a release at cluster scope there waits for the MMAs it has just issued.
-          if (warp == 2 && lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&st->landed[stage]), 1));
-        } else {
-          mbar_wait_backoff(&st->landed[stage], phase);
-        }
-        if (tn == 0) {
-          const int64_t rr0 = r0 + static_cast<int64_t>(it) * 64;
-          const uint8_t* tile = stages + stage * kW2StageBytes + box_off;
-          float2 acc[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = rg * 8 + i;
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-            if (p.bf16) {
-              add_pair_f32_w2<true>(v.x, acc[0]); add_pair_f32_w2<true>(v.y, acc[1]);
-              add_pair_f32_w2<true>(v.z, acc[2]); add_pair_f32_w2<true>(v.w, acc[3]);
-            } else {
-              add_pair_f32_w2<false>(v.x, acc[0]); add_pair_f32_w2<false>(v.y, acc[1]);
-              add_pair_f32_w2<false>(v.z, acc[2]); add_pair_f32_w2<false>(v.w, acc[3]);
-            }
-          }
-          // the warp's two row groups (lanes l and l ^ 16) meet in the lower half
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[e].x += __shfl_xor_sync(0xffffffffu, acc[e].x, 16);
-            acc[e].y += __shfl_xor_sync(0xffffffffu, acc[e].y, 16);
-          }
-          const int64_t g = rr0 / p.rows_per_group;
-          if (g != cur_g) { flush(); cur_g = g; }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { gsum[2 * e] += acc[e].x; gsum[2 * e + 1] += acc[e].y; }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st->empty[stage]);
-        if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
-      }
-      if (tn == 0) flush();
-    }
     if (nstage_iters > 0) {
       mbar_wait(&st->tmem_full, 0);
       tc_fence_after();
@@ -379,12 +297,7 @@ int tc_wgrad_pair(const pcadv_wgrad_args& a, cudaStream_t s) {
   p.bf16 = dt == PCADV_BF16 ? 1 : 0;
   p.dw = a.dw; p.ld_dw = a.ld_dw; p.scale = a.scale;
   p.vec_red = (a.ld_dw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.dw) & 15) == 0) ? 1 : 0;
-  // The per-cloud column sums are NOT fused here: they would put a cross-CTA hand-off (stage landed
-  // -> peer's sum warps -> peer's stage release) into the ring and cost more (0.77 vs 0.49 ms on fc1)
-  // than the separate 0.1 ms pass over dz below.  The in-kernel path is kept for reference.
-  const bool fuse_sums = false;
-  p.dgroup_bias = fuse_sums ? a.dgroup_bias : nullptr;
-  p.rows_per_group = a.rows_per_group > 0 ? a.rows_per_group : a.rows;
+
   const size_t smem = 1024 + static_cast<size_t>(kW2Stages) * kW2StageBytes + sizeof(W2Tail) + 16;
   static bool attr_done = false;
   if (!attr_done) {
@@ -395,7 +308,7 @@ int tc_wgrad_pair(const pcadv_wgrad_args& a, cudaStream_t s) {
   const int grid = 2 * p.tiles_n * p.splits;            // one work item per CTA pair, one wave
   tc_wgrad_pair_kernel<<<grid, kW2Threads, smem, s>>>(maps, p);
   PCADV_LAUNCHED();
-  if (a.dgroup_bias && !fuse_sums) {
+  if (a.dgroup_bias) {                                   // per-cloud column sums: a separate pass (see top)
     if (int rc = launch_group_colsum(a.dz, a.dz_dtype, a.ld_dz, a.rows, a.n, a.rows_per_group, a.dgroup_bias, s))
       return rc;
   }
