@@ -70,12 +70,25 @@ class HeadArgs(C.Structure):
     ]
 
 
+class ChainLayer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("ldw", C.c_int64), ("n", C.c_int32), ("act", C.c_int32),
+                ("slope", C.c_float), ("bias", C.c_void_p), ("out", C.c_void_p), ("ld_out", C.c_int64),
+                ("bits_out", C.c_void_p), ("ld_bits", C.c_int64)]
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("x", C.c_void_p), ("ldx", C.c_int64), ("k0", C.c_int32),
+                ("dtype", C.c_int32), ("num_layers", C.c_int32), ("layer", ChainLayer * 4),
+                ("rowmax_key", C.c_void_p)]
+
+
 HEAD_CE, HEAD_LSM = 0, 1
 
 # every symbol include/pcadv.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pcadv_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "pcadv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "pcadv_chain": (C.c_int, [C.POINTER(ChainArgs), C.c_void_p]),
     "pcadv_max_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "pcadv_maxpool_bwd": (C.c_int, [C.POINTER(MaxBwdArgs), C.c_void_p]),

@@ -100,16 +100,53 @@ def _compute_weight(prec, w32, k_list, n):
     return w32
 
 
+def _chain_run(prec, x, run, rowmax=False, want_bits=True):
+    """``run`` consecutive layers on x through one pcadv_chain launch."""
+    ws, k = [], x.shape[1]
+    for L in run:
+        ws.append((compute_weight(prec, L.w, [k], L.w.shape[0]), L.b, L.act, L.slope))
+        k = L.w.shape[0]
+    return ops.chain(x, ws, rowmax=rowmax, want_bits=want_bits)
+
+
+def chain_run_length(prec, x, layers, start, allow_last=True):
+    """How many layers from ``start`` on can go into one chained launch (0 = none): tensor-core
+    engine, 16-bit single-segment input, every width a multiple of 64 within the kernel's budget."""
+    if prec.engine != ENGINE_TC or prec.act_dtype == torch.float32:
+        return 0
+    widths = [x.shape[1]]
+    best = 0
+    stop = len(layers) if allow_last else len(layers) - 1
+    for j in range(start, min(stop, start + 4)):
+        widths.append(layers[j].w.shape[0])
+        if len(widths) >= 3 and ops.chain_eligible(x, widths):
+            best = j - start + 1
+    return best
+
+
 def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, group_bias=None,
                   bits=None):
     """Run ``layers`` on the K-concat of ``x_segs``.  ``group_bias`` (per-cloud
     bias) applies to the first layer.  Returns the list of layer outputs.  ``bits``: a list that
     receives, per layer, the 1-bit map [y > 0] of an activated output (or None where the layer
-    cannot emit it) -- what the backward reads instead of the 16-bit activation."""
+    cannot emit it) -- what the backward reads instead of the 16-bit activation.  Consecutive
+    narrow layers (widths <= 256, multiples of 64) go through ``pcadv_chain`` in one launch."""
     ys = []
     segs = list(x_segs)
-    for i, L in enumerate(layers):
+    i = 0
+    while i < len(layers):
+        L = layers[i]
         last = i == len(layers) - 1
+        if len(segs) == 1 and not (i == 0 and group_bias is not None):
+            run = chain_run_length(prec, segs[0], layers, i, allow_last=not final_fp32)
+            if run >= 2:
+                outs, bts, _ = _chain_run(prec, segs[0], layers[i:i + run], want_bits=bits is not None)
+                ys.extend(outs)
+                if bits is not None:
+                    bits.extend(bts)
+                segs = [outs[-1]]
+                i += run
+                continue
         n = L.w.shape[0]
         w = compute_weight(prec, L.w, [s.shape[1] for s in segs], n)
         out_dtype = torch.float32 if (last and final_fp32) else prec.act_dtype
@@ -124,6 +161,7 @@ def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, grou
         if bits is not None:
             bits.append(b)
         segs = [y]
+        i += 1
     return ys
 
 

@@ -101,11 +101,23 @@ class PointMLPFunction(torch.autograd.Function):
         if gb is not None:
             gb = gb.contiguous().float()
         ybits = []
-        ys = chain_forward(prec, [x_in], body, final_fp32=(spec.reduce is None),
-                           rows_per_group=spec.group if gb is not None else 0,
-                           group_bias=gb, bits=ybits) if body else []
         red_val = red_idx = None
-        if spec.reduce is not None:
+        fused_red = False
+        if spec.reduce == "channels" and gb is None and body and \
+                _chain.chain_run_length(prec, x_in, layers, 0) == len(layers):
+            # the whole discriminator trunk + max over channels in one chained launch
+            outs, bts, rkey = _chain._chain_run(prec, x_in, layers, rowmax=True)
+            ys, ybits = outs[:-1], bts[:-1]
+            red_val, red_idx = ops.max_finalize(rkey, layers[-1].act, layers[-1].slope)
+            out = red_val
+            fused_red = True
+        else:
+            ys = chain_forward(prec, [x_in], body, final_fp32=(spec.reduce is None),
+                               rows_per_group=spec.group if gb is not None else 0,
+                               group_bias=gb, bits=ybits) if body else []
+        if fused_red:
+            pass
+        elif spec.reduce is not None:
             L = layers[-1]
             src = ys[-1] if ys else x_in
             w = compute_weight(prec, L.w, [src.shape[1]], L.w.shape[0])

@@ -207,6 +207,60 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
     return out, ckey, rkey
 
 
+def chain_eligible(x, widths):
+    """Shapes ``chain`` takes: a 16-bit TMA-compatible input and 2..4 layers whose widths (input
+    included) are multiples of 64 in [64, 256]."""
+    if x.dtype not in (torch.float16, torch.bfloat16) or x.dim() != 2 or x.shape[0] < 128:
+        return False
+    if x.stride(1) != 1 or x.stride(0) % 8 or x.data_ptr() % 16:
+        return False
+    if not 2 <= len(widths) - 1 <= 4:
+        return False
+    if not all(w % 64 == 0 and 64 <= w <= 256 for w in widths):
+        return False
+    # shared-memory budget of tc_chain.cu: >= 2 ring stages + one [128 x max_n] tile per epilogue half
+    max_n = max(widths[1:])
+    smem = 1024 + 2 * (16384 + max_n * 128) + 2 * 128 * max_n * 2 + 4096 + 8192 + 256
+    return smem <= 232448
+
+
+def chain(x, layers, *, rowmax=False, want_bits=True):
+    """See ``pcadv_chain``.  layers: [(w16 [n, k], bias | None, act, slope)] (weights already in the
+    16-bit compute dtype).  Returns (outputs [list of [rows, n] 16-bit tensors; the last one None
+    with ``rowmax``], sign-bit maps [list, None where not produced], rowmax key | None)."""
+    a = _lib.ChainArgs()
+    rows, k0 = x.shape
+    a.rows, a.x, a.ldx, a.k0, a.dtype, a.num_layers = rows, C.c_void_p(x.data_ptr()), x.stride(0), k0, _DT[x.dtype], len(layers)
+    outs, bits = [], []
+    dev = x.device
+    for l, (w, b, act, slope) in enumerate(layers):
+        n = w.shape[0]
+        L = a.layer[l]
+        L.w, L.ldw, L.n, L.act, L.slope = C.c_void_p(w.data_ptr()), w.stride(0), n, act, float(slope)
+        L.bias = _f32(b, n) if b is not None else None
+        last = l == len(layers) - 1
+        if last and rowmax:
+            outs.append(None); bits.append(None)
+            continue
+        o = torch.empty((rows, n), dtype=x.dtype, device=dev)
+        L.out, L.ld_out = C.c_void_p(o.data_ptr()), n
+        outs.append(o)
+        if want_bits and act != ACT_NONE:
+            bt = new_bits(rows, n, dev)
+            L.bits_out, L.ld_bits = C.c_void_p(bt.data_ptr()), bt.stride(0)
+            bits.append(bt)
+        else:
+            bits.append(None)
+    rkey = None
+    if rowmax:
+        rkey = torch.zeros((rows,), dtype=torch.int64, device=dev)
+        a.rowmax_key = C.c_void_p(rkey.data_ptr())
+    if rows > 0:
+        _call("chain:k%d:%s%s" % (k0, "-".join(str(w.shape[0]) for w, _, _, _ in layers), ":rowmax" if rowmax else ""),
+              _lib.lib().pcadv_chain, C.byref(a), _stream())
+    return outs, bits, rkey
+
+
 def bits_eligible(prec, segs, w, n):
     """True when a layer can emit / consume the 1-bit activation mask: tensor-core engine,
     16-bit storage, n a multiple of 64."""

@@ -111,6 +111,44 @@ typedef struct pcadv_linear_args {
 int pcadv_linear(const pcadv_linear_args* a, void* stream);
 
 /*
+ * pcadv_chain: up to four consecutive pointwise layers in one kernel,
+ *   y_0 = act_0(x W_0^T + b_0),  y_l = act_l(y_{l-1} W_l^T + b_l)
+ * -- the F.relu(self.convK(x)) chains of models/pointnet.py:292-300 and
+ * models/discriminator.py:64-67.  Every width (k0 and each n) is a multiple of 64 in [64, 256],
+ * x / weights / outputs are 16-bit (`dtype`), accumulation is fp32.  Each layer's output is written
+ * once (`out`, with its sign-bit map `bits_out`, see pcadv_linear) but never read back: the next
+ * layer multiplies the tile straight out of shared memory.  With `rowmax_key` the LAST layer stores
+ * no output; its pre-activation maximum over the channels goes to rowmax_key[r] (packed key, see
+ * pcadv_linear / pcadv_max_finalize) -- torch.max over channels at models/discriminator.py:71.
+ */
+#define PCADV_CHAIN_MAX_LAYERS 4
+typedef struct pcadv_chain_layer {
+  const void* w;              /* [n, k] row-major, k = previous layer's n (k0 for layer 0) */
+  int64_t ldw;
+  int32_t n;
+  int32_t act;
+  float slope;
+  const float* bias;          /* [n] fp32 or NULL */
+  void* out;                  /* [rows, n] 16-bit; may be NULL only for the last layer */
+  int64_t ld_out;
+  uint32_t* bits_out;         /* [rows, n / 32] or NULL */
+  int64_t ld_bits;
+} pcadv_chain_layer;
+
+typedef struct pcadv_chain_args {
+  int64_t rows;
+  const void* x;              /* [rows, k0] */
+  int64_t ldx;
+  int32_t k0;
+  int32_t dtype;              /* PCADV_F16 / PCADV_BF16 */
+  int32_t num_layers;         /* 2 .. PCADV_CHAIN_MAX_LAYERS */
+  pcadv_chain_layer layer[PCADV_CHAIN_MAX_LAYERS];
+  unsigned long long* rowmax_key;   /* [rows] or NULL */
+} pcadv_chain_args;
+
+int pcadv_chain(const pcadv_chain_args* a, void* stream);
+
+/*
  * pcadv_wgrad: dw[c, koff_seg + k] += scale * sum_r dz[r, c] * seg[r, k]
  *              dbias[c]            += scale * sum_r dz[r, c]
  *              dgroup_bias[g, c]   += sum_{r in cloud g} dz[r, c]   (NOT scaled)

@@ -169,3 +169,35 @@ def test_tc_wgrad_cta_pair(dtype, rows, ks, rpg):
     assert rel_err(dw, ref) < 1e-5
     if rpg:
         assert rel_err(dgb, dz.double().view(rows // rpg, rpg, n).sum(1)) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,widths,rowmax", [(1000, [64, 128, 128, 128], False), (4133, [64, 64, 64, 64, 128], True),
+                                                (129, [256, 128, 64], False), (40000, [128, 128, 128, 64, 64], False)])
+def test_tc_chain(dtype, rows, widths, rowmax):
+    """pcadv_chain (layers multiplied out of shared memory) against the same layers run one by one
+    through pcadv_linear: identical stored activations, sign bits and row-max."""
+    x = _rand((rows, widths[0]), 61, dtype)
+    layers = []
+    for l in range(len(widths) - 1):
+        w = _rand((widths[l + 1], widths[l]), 62 + l, dtype, 1.5 / widths[l] ** 0.5)
+        b = _rand((widths[l + 1],), 70 + l, torch.float32, 0.1)
+        layers.append((w, b, ACT_RELU, 0.0))
+    assert ops.chain_eligible(x, widths)
+    assert not ops.chain_eligible(x, [widths[0], 256, 256])        # two 256-wide tiles do not fit
+    outs, bits, rkey = ops.chain(x, layers, rowmax=rowmax)
+    cur = x
+    for l, (w, b, act, slope) in enumerate(layers):
+        last = l == len(layers) - 1
+        if last and rowmax:
+            _, _, rk = ops.linear([cur], w, bias=b, want_out=False, rowmax=True, engine=ENGINE_TC)
+            v1, i1 = ops.max_finalize(rkey, ACT_RELU)
+            v2, i2 = ops.max_finalize(rk, ACT_RELU)
+            assert torch.equal(v1, v2) and torch.equal(i1, i2)
+            assert outs[l] is None
+            break
+        bt = ops.new_bits(rows, widths[l + 1], DEV)
+        ref, _, _ = ops.linear([cur], w, bias=b, act=act, out_dtype=dtype, engine=ENGINE_TC, bits_out=bt)
+        assert torch.equal(outs[l], ref), l
+        assert torch.equal(bits[l], bt), l
+        cur = ref
