@@ -79,7 +79,7 @@ class ChainLayer(C.Structure):
 class ChainArgs(C.Structure):
     _fields_ = [("rows", C.c_int64), ("x", C.c_void_p), ("ldx", C.c_int64), ("k0", C.c_int32),
                 ("dtype", C.c_int32), ("num_layers", C.c_int32), ("layer", ChainLayer * 4),
-                ("rowmax_key", C.c_void_p)]
+                ("rowmax_key", C.c_void_p), ("out_f32", C.c_void_p), ("n_f32", C.c_int32)]
 
 
 HEAD_CE, HEAD_LSM = 0, 1

@@ -44,6 +44,7 @@ struct ChainParams {
   int num_layers;
   int k[kChainMaxLayers];                     // multiples of 64, <= 256
   int n[kChainMaxLayers];                     // multiples of 64, <= 256 (n[l] == k[l + 1])
+  int nvalid[kChainMaxLayers];                // real output channels (< n only for the fp32 last layer)
   int act[kChainMaxLayers];
   float slope[kChainMaxLayers];
   uint32_t idesc[kChainMaxLayers];
@@ -52,6 +53,9 @@ struct ChainParams {
   uint32_t* bits_out[kChainMaxLayers];        // sign-bit maps (or NULL)
   int64_t ld_bits[kChainMaxLayers];
   unsigned long long* rowmax_key;             // last layer: max over channels instead of an output
+  float* out_f32;                             // last layer: fp32 rows [rows, n_f32] (contiguous) instead
+  int n_f32;                                  //   of a 16-bit TMA-stored output (n_f32 <= 64 <= n[last])
+  int serial;                                 // one tile in flight, both halves split its steps (wide chains)
   int nstages, stage_bytes, h_bytes;
   int bf16;
 };
@@ -131,7 +135,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&st->acc_full[h], 1);
-      mbar_init(&st->in_ready[h], 4);
+      mbar_init(&st->in_ready[h], p.serial ? 8 : 4);
     }
     fence_barrier_init();
   }
@@ -139,7 +143,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   // every layer's bias, once: all tiles cover all columns (n <= 256)
   for (int e = threadIdx.x; e < NL * kMaxTileN; e += kChainThreads) {
     const int l = e / kMaxTileN, c = e - l * kMaxTileN;
-    L.bias[e] = (c < p.n[l] && p.bias[l]) ? __ldg(p.bias[l] + c) : 0.f;
+    L.bias[e] = (c < p.nvalid[l] && p.bias[l]) ? __ldg(p.bias[l] + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -147,17 +151,20 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   const uint32_t tmem_base = st->tmem_base;
   // tiles of this CTA: i = 0, 1, 2, ... -> global tile blockIdx.x + i * gridDim.x, half i & 1
   const int64_t my_tiles = p.tiles > blockIdx.x ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // serial mode (chains with a 256-wide intermediate: one shared-memory tile only): one tile in
+  // flight in accumulator / tile 0, and the two epilogue halves take alternate 64-column steps of it
+  const int tiles_in_flight = p.serial ? 1 : 2;
 
   if (warp == 0) {
     // ================= TMA producer: same (pair, layer, half, chunk) order as the MMA thread =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t i0 = 0; i0 < my_tiles; i0 += 2) {
+      for (int64_t i0 = 0; i0 < my_tiles; i0 += tiles_in_flight) {
         for (int l = 0; l < NL; ++l) {
           const int chunks = p.k[l] >> 6;
           const uint32_t tx = static_cast<uint32_t>((l == 0 ? kTileM : 0) + p.n[l]) * kBlockK * 2;
-          for (int h = 0; h < 2 && i0 + h < my_tiles; ++h) {
+          for (int h = 0; h < tiles_in_flight && i0 + h < my_tiles; ++h) {
             const int32_t m0 = static_cast<int32_t>((blockIdx.x + (i0 + h) * gridDim.x) * kTileM);
             for (int c = 0; c < chunks; ++c) {
               mbar_wait_backoff(&st->empty[stage], phase ^ 1);
@@ -177,10 +184,10 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ready_par[2] = {0, 0};                    // parity of the next in_ready wait per half
-      for (int64_t i0 = 0; i0 < my_tiles; i0 += 2) {
+      for (int64_t i0 = 0; i0 < my_tiles; i0 += tiles_in_flight) {
         for (int l = 0; l < NL; ++l) {
           const int chunks = p.k[l] >> 6;
-          for (int h = 0; h < 2 && i0 + h < my_tiles; ++h) {
+          for (int h = 0; h < tiles_in_flight && i0 + h < my_tiles; ++h) {
             // H[h] holds the previous layer's output (l > 0) and the accumulator has been drained
             mbar_wait_backoff(&st->in_ready[h], ready_par[h] ^ 1);
             ready_par[h] ^= 1;
@@ -206,16 +213,17 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;
+    const int buf = p.serial ? 0 : half;                 // accumulator buffer / H tile this warp works on
     const int lane_row = quarter * 32 + lane;
-    const uint32_t h_base = smem_u32(L.H + half * p.h_bytes);
+    const uint32_t h_base = smem_u32(L.H + buf * p.h_bytes);
     // this thread's 128-byte row inside a step's [128 rows x 128 B] tile of H
     const uint32_t row_off = static_cast<uint32_t>(quarter) * 4096u + static_cast<uint32_t>(lane) * 128u;
     const uint32_t bits_s = smem_u32(L.bits + ew * 32 * kChainBitsWords);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                            static_cast<uint32_t>(half * kMaxTileN);
+                            static_cast<uint32_t>(buf * kMaxTileN);
     uint32_t full_par = 0;
-    for (int64_t i = half; i < my_tiles; i += 2) {
+    for (int64_t i = p.serial ? 0 : half; i < my_tiles; i += tiles_in_flight) {
       const int64_t tm = blockIdx.x + i * gridDim.x;
       const int64_t r = tm * kTileM + lane_row;
       const bool r_ok = r < p.rows;
@@ -224,21 +232,26 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int steps = p.n[l] >> 6;
         const bool last = l == NL - 1;
         const bool rowmax = last && p.rowmax_key != nullptr;
+        const bool f32out = last && p.out_f32 != nullptr;
         const bool want_bits = p.bits_out[l] != nullptr;
         const int act = p.act[l];
         const float slope = p.slope[l];
         const uint32_t bias_a = smem_u32(L.bias + l * kMaxTileN);
-        mbar_wait(&st->acc_full[half], full_par);
+        mbar_wait(&st->acc_full[buf], full_par);
         full_par ^= 1;
         tc_fence_after();
         // H[half] was the A operand of the MMAs that just completed; the TMA stores issued from it
         // for the previous layer must have finished reading before it is overwritten
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
+        // the fp32 row staging of a warp overlaps slabs other warps stored from: everybody's stores
+        // must have been read out first
+        if (f32out) named_barrier_sync(1 + buf, p.serial ? 256 : 128);
         float best = -INFINITY;
         int best_col = 0;
 #pragma unroll 1
         for (int step = 0; step < steps; ++step) {
+          if (p.serial && (step & 1) != half) continue;    // the other half's step
           const uint32_t srow = h_base + static_cast<uint32_t>(step) * kABytes + row_off;
           uint32_t raw[2][32];
           tmem_ld32_issue(taddr0 + step * 64, raw[0]);
@@ -270,6 +283,16 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               }
               continue;
             }
+            if (f32out) {
+              // fp32 rows, compact [32 rows][n_f32] staging in this warp's 8 KB of the (now free) tile
+              const uint32_t crow = h_base + static_cast<uint32_t>(quarter) * 8192u +
+                                    static_cast<uint32_t>(lane * p.n_f32 + step * 64 + h2 * 32) * 4u;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (step * 64 + h2 * 32 + j < p.n_f32)
+                  asm volatile("st.shared.f32 [%0], %1;" ::"r"(crow + j * 4), "f"(v[j]) : "memory");
+              continue;
+            }
             if (act == PCADV_ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -291,7 +314,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             for (int q = 0; q < 4; ++q)
               c_sts128(srow + (((h2 * 4 + q) ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
-          if (rowmax) continue;
+          if (rowmax || f32out) continue;
           if (want_bits) c_sts64(bits_s + (lane * kChainBitsWords + 2 * step) * 4, obits[0], obits[1]);
           fence_proxy_async();                             // slab visible to the TMA store and the next MMA
           __syncwarp();
@@ -302,12 +325,46 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           }
         }
         if (rowmax) {
-          if (r_ok) p.rowmax_key[r] = pack_key(best, static_cast<uint32_t>(best_col));
+          if (r_ok) {
+            const unsigned long long key = pack_key(best, static_cast<uint32_t>(best_col));
+            if (p.serial) atomicMax(&p.rowmax_key[r], key);    // the two halves hold alternate steps
+            else p.rowmax_key[r] = key;
+          }
+        } else if (f32out) {
+          // n_f32 <= 64: one step, taken by half 0 in serial mode
+          if (!p.serial || half == 0) {
+            const int64_t wr0 = tm * kTileM + quarter * 32;
+            int64_t nrows = p.rows - wr0;
+            nrows = nrows > 32 ? 32 : nrows;
+            if (nrows > 0) {
+              const uint32_t bytes = static_cast<uint32_t>(nrows * p.n_f32 * 4);
+              float* gdst = p.out_f32 + wr0 * p.n_f32;
+              const uint32_t ssrc = h_base + static_cast<uint32_t>(quarter) * 8192u;
+              if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(ssrc), "r"(bytes) : "memory");
+                  bulk_commit_group();
+                }
+              } else {
+                __syncwarp();
+                for (uint32_t e = lane; e < bytes / 4; e += 32) {
+                  float val;
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(ssrc + e * 4));
+                  gdst[e] = val;
+                }
+                __syncwarp();
+              }
+            }
+          }
         } else if (want_bits) {
           __syncwarp();
           const int64_t wr0 = tm * kTileM + quarter * 32;
           for (int e = lane; e < 32 * steps; e += 32) {
             const int rr = e / steps, uu = e - rr * steps;
+            if (p.serial && (uu & 1) != half) continue;    // the other half staged (and flushes) that step
             if (wr0 + rr < p.rows) {
               const uint2 w2 = c_lds64(bits_s + (rr * kChainBitsWords + 2 * uu) * 4);
               *reinterpret_cast<uint2*>(p.bits_out[l] + (wr0 + rr) * p.ld_bits[l] + 2 * uu) = w2;
@@ -318,7 +375,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         // H[half] = this layer's output, accumulator drained: the next MMA of this half may go
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&st->in_ready[half]);
+        if (lane == 0) mbar_arrive(&st->in_ready[buf]);
       }
     }
     if (lane == 0) bulk_wait_group<0>();
@@ -349,6 +406,11 @@ extern "C" int pcadv_chain(const pcadv_chain_args* a, void* stream) {
   p.tiles = (a->rows + kTileM - 1) / kTileM;
   p.bf16 = dt == PCADV_BF16 ? 1 : 0;
   p.rowmax_key = a->rowmax_key;
+  p.out_f32 = a->out_f32; p.n_f32 = a->n_f32;
+  PCADV_CHECK_ARG(!(a->rowmax_key && a->out_f32), "pcadv_chain: rowmax_key and out_f32 are exclusive");
+  PCADV_CHECK_ARG(!a->out_f32 || (a->n_f32 >= 1 && a->n_f32 <= 64 && a->layer[a->num_layers - 1].n == 64 &&
+                                  (reinterpret_cast<uintptr_t>(a->out_f32) & 3) == 0),
+                  "pcadv_chain: out_f32 needs a last layer of (padded) width 64 and n_f32 <= 64");
   int max_n = 0, max_kn = 0;
   for (int l = 0; l < a->num_layers; ++l) {
     const pcadv_chain_layer& Ly = a->layer[l];
@@ -358,11 +420,14 @@ extern "C" int pcadv_chain(const pcadv_chain_args* a, void* stream) {
                     "pcadv_chain: layer %d: k and n must be multiples of 64 in [64, 256] (k=%d n=%d)", l, k, Ly.n);
     PCADV_CHECK_ARG(Ly.w && tma_compatible(Ly.w, dt, Ly.ldw), "pcadv_chain: layer %d weight not TMA-compatible", l);
     PCADV_CHECK_ARG(last || Ly.out, "pcadv_chain: every layer but the last must store its output");
-    PCADV_CHECK_ARG(!(last && a->rowmax_key) || (!Ly.out && !Ly.bits_out), "pcadv_chain: row-max layer has no output");
-    PCADV_CHECK_ARG(last ? (Ly.out || a->rowmax_key) : true, "pcadv_chain: last layer needs an output or rowmax_key");
+    PCADV_CHECK_ARG(!(last && (a->rowmax_key || a->out_f32)) || (!Ly.out && !Ly.bits_out),
+                    "pcadv_chain: a row-max / fp32 last layer has no 16-bit output");
+    PCADV_CHECK_ARG(last ? (Ly.out || a->rowmax_key || a->out_f32) : true,
+                    "pcadv_chain: last layer needs an output, rowmax_key or out_f32");
     p.k[l] = k; p.n[l] = Ly.n; p.act[l] = Ly.act; p.slope[l] = Ly.slope; p.bias[l] = Ly.bias;
+    p.nvalid[l] = (last && a->out_f32) ? a->n_f32 : Ly.n;     // rows the weight / bias really have
     p.idesc[l] = make_idesc(kTileM, Ly.n, dt == PCADV_BF16, false, false);
-    if (int rc = encode_tmap_2d(&maps.w[l], Ly.w, dt, Ly.n, k, Ly.ldw, kBlockK, Ly.n)) return rc;
+    if (int rc = encode_tmap_2d(&maps.w[l], Ly.w, dt, p.nvalid[l], k, Ly.ldw, kBlockK, Ly.n)) return rc;
     p.has_out[l] = Ly.out ? 1 : 0;
     if (Ly.out) {
       PCADV_CHECK_ARG(tma_compatible(Ly.out, dt, Ly.ld_out), "pcadv_chain: layer %d output not TMA-storable", l);
@@ -371,13 +436,18 @@ extern "C" int pcadv_chain(const pcadv_chain_args* a, void* stream) {
     PCADV_CHECK_ARG(!Ly.bits_out || (Ly.ld_bits % 2 == 0 && (reinterpret_cast<uintptr_t>(Ly.bits_out) & 7) == 0),
                     "pcadv_chain: layer %d sign-bit rows must be 8-byte aligned", l);
     p.bits_out[l] = Ly.bits_out; p.ld_bits[l] = Ly.ld_bits;
-    if (!(last && a->rowmax_key)) max_n = Ly.n > max_n ? Ly.n : max_n;
+    if (!(last && (a->rowmax_key || a->out_f32))) max_n = Ly.n > max_n ? Ly.n : max_n;
     max_kn = Ly.n > max_kn ? Ly.n : max_kn;
   }
   PCADV_CHECK_ARG(tma_compatible(a->x, dt, a->ldx), "pcadv_chain: input not TMA-compatible");
   if (int rc = encode_tmap_2d(&maps.x, a->x, dt, a->rows, a->k0, a->ldx, kBlockK, kTileM)) return rc;
+  if (a->out_f32 && max_n < 128) max_n = 128;                   // 4 x 8 KB of fp32 row staging
   p.h_bytes = kTileM * (max_n > 64 ? max_n : 64) * 2;           // one [128 x max_n] tile per half
   p.stage_bytes = kABytes + max_kn * kBlockK * 2;
+  // two tiles in flight need two tiles of shared memory; chains with a 256-wide intermediate run
+  // one tile at a time and let both epilogue halves split its steps
+  p.serial = chain_smem_bytes(2, p.stage_bytes, p.h_bytes) > static_cast<size_t>(kChainSmemMax) ? 1 : 0;
+  if (p.serial) p.h_bytes /= 2;                                 // carve_chain lays out 2 * h_bytes
   int nst = kChainMaxStages;
   while (nst > 2 && chain_smem_bytes(nst, p.stage_bytes, p.h_bytes) > static_cast<size_t>(kChainSmemMax)) --nst;
   p.nstages = nst;

@@ -6,6 +6,8 @@ models/discriminator.py:22-24, :44-48, :64-67).  Activations are point-major
 ``[rows, channels]`` matrices; ``dz`` always means the gradient with respect
 to a layer's PRE-activation output, which is what dgrad and wgrad consume.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -100,28 +102,39 @@ def _compute_weight(prec, w32, k_list, n):
     return w32
 
 
-def _chain_run(prec, x, run, rowmax=False, want_bits=True):
+_CHAIN_ON = os.environ.get("PCADV_CHAIN", "1") != "0"      # tuning aid: per-layer launches only
+
+
+def _chain_run(prec, x, run, rowmax=False, want_bits=True, last_f32=False):
     """``run`` consecutive layers on x through one pcadv_chain launch."""
     ws, k = [], x.shape[1]
     for L in run:
         ws.append((compute_weight(prec, L.w, [k], L.w.shape[0]), L.b, L.act, L.slope))
-        k = L.w.shape[0]
-    return ops.chain(x, ws, rowmax=rowmax, want_bits=want_bits)
+        k = (L.w.shape[0] + 63) // 64 * 64
+    return ops.chain(x, ws, rowmax=rowmax, want_bits=want_bits, last_f32=last_f32)
 
 
-def chain_run_length(prec, x, layers, start, allow_last=True):
-    """How many layers from ``start`` on can go into one chained launch (0 = none): tensor-core
-    engine, 16-bit single-segment input, every width a multiple of 64 within the kernel's budget."""
-    if prec.engine != ENGINE_TC or prec.act_dtype == torch.float32:
-        return 0
+def chain_run_length(prec, x, layers, start, final_fp32=False):
+    """(how many layers from ``start`` on can go into one chained launch (0 = none), whether the
+    run ends with the fp32 last layer): tensor-core engine, 16-bit single-segment input, every
+    width a multiple of 64 within the kernel's budget; an fp32 last layer may be up to 64 wide."""
+    if prec.engine != ENGINE_TC or prec.act_dtype == torch.float32 or not _CHAIN_ON:
+        return 0, False
     widths = [x.shape[1]]
-    best = 0
-    stop = len(layers) if allow_last else len(layers) - 1
-    for j in range(start, min(stop, start + 4)):
-        widths.append(layers[j].w.shape[0])
-        if len(widths) >= 3 and ops.chain_eligible(x, widths):
-            best = j - start + 1
-    return best
+    best, best_f32 = 0, False
+    for j in range(start, min(len(layers), start + 4)):
+        n = layers[j].w.shape[0]
+        f32 = final_fp32 and j == len(layers) - 1
+        if f32:
+            if n > 64 or layers[j].act != ACT_NONE:
+                break
+            n = 64
+        widths.append(n)
+        if len(widths) >= 3 and ops.chain_eligible(x, widths, last_f32=f32):
+            best, best_f32 = j - start + 1, f32
+        if n % 64:
+            break
+    return best, best_f32
 
 
 def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, group_bias=None,
@@ -138,9 +151,10 @@ def chain_forward(prec, x_segs, layers, final_fp32=False, rows_per_group=0, grou
         L = layers[i]
         last = i == len(layers) - 1
         if len(segs) == 1 and not (i == 0 and group_bias is not None):
-            run = chain_run_length(prec, segs[0], layers, i, allow_last=not final_fp32)
+            run, run_f32 = chain_run_length(prec, segs[0], layers, i, final_fp32=final_fp32)
             if run >= 2:
-                outs, bts, _ = _chain_run(prec, segs[0], layers[i:i + run], want_bits=bits is not None)
+                outs, bts, _ = _chain_run(prec, segs[0], layers[i:i + run], want_bits=bits is not None,
+                                          last_f32=run_f32)
                 ys.extend(outs)
                 if bits is not None:
                     bits.extend(bts)

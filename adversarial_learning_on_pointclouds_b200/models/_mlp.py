@@ -104,7 +104,7 @@ class PointMLPFunction(torch.autograd.Function):
         red_val = red_idx = None
         fused_red = False
         if spec.reduce == "channels" and gb is None and body and \
-                _chain.chain_run_length(prec, x_in, layers, 0) == len(layers):
+                _chain.chain_run_length(prec, x_in, layers, 0)[0] == len(layers):
             # the whole discriminator trunk + max over channels in one chained launch
             outs, bts, rkey = _chain._chain_run(prec, x_in, layers, rowmax=True)
             ys, ybits = outs[:-1], bts[:-1]

@@ -207,9 +207,10 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
     return out, ckey, rkey
 
 
-def chain_eligible(x, widths):
+def chain_eligible(x, widths, last_f32=False, allow_serial=False):
     """Shapes ``chain`` takes: a 16-bit TMA-compatible input and 2..4 layers whose widths (input
-    included) are multiples of 64 in [64, 256]."""
+    included) are multiples of 64 in [64, 256] (``widths`` lists the padded widths; with
+    ``last_f32`` the last layer is at most 64 wide and leaves as fp32 rows)."""
     if x.dtype not in (torch.float16, torch.bfloat16) or x.dim() != 2 or x.shape[0] < 128:
         return False
     if x.stride(1) != 1 or x.stride(0) % 8 or x.data_ptr() % 16:
@@ -218,16 +219,25 @@ def chain_eligible(x, widths):
         return False
     if not all(w % 64 == 0 and 64 <= w <= 256 for w in widths):
         return False
-    # shared-memory budget of tc_chain.cu: >= 2 ring stages + one [128 x max_n] tile per epilogue half
-    max_n = max(widths[1:])
-    smem = 1024 + 2 * (16384 + max_n * 128) + 2 * 128 * max_n * 2 + 4096 + 8192 + 256
+    if last_f32 and widths[-1] != 64:
+        return False
+    # shared-memory budget of tc_chain.cu: >= 2 ring stages + a [128 x max_n] tile per epilogue half.
+    # Chains that only fit with ONE tile (a 256-wide stored output) run in the kernel's serial mode,
+    # which measured slower than separate launches (0.53 vs 0.41 ms for fc2 -> fc3 -> fc4 at 2^20
+    # points), so the models do not ask for it.
+    max_n = max(widths[1:-1] + ([] if last_f32 else widths[-1:]))
+    if last_f32:
+        max_n = max(max_n, 128)
+    tiles = 1 if allow_serial else 2
+    smem = 1024 + 2 * (16384 + max(widths[1:]) * 128) + tiles * 128 * max_n * 2 + 4096 + 8192 + 256
     return smem <= 232448
 
 
-def chain(x, layers, *, rowmax=False, want_bits=True):
+def chain(x, layers, *, rowmax=False, want_bits=True, last_f32=False):
     """See ``pcadv_chain``.  layers: [(w16 [n, k], bias | None, act, slope)] (weights already in the
     16-bit compute dtype).  Returns (outputs [list of [rows, n] 16-bit tensors; the last one None
-    with ``rowmax``], sign-bit maps [list, None where not produced], rowmax key | None)."""
+    with ``rowmax``, fp32 [rows, n] with ``last_f32``], sign-bit maps [list, None where not
+    produced], rowmax key | None)."""
     a = _lib.ChainArgs()
     rows, k0 = x.shape
     a.rows, a.x, a.ldx, a.k0, a.dtype, a.num_layers = rows, C.c_void_p(x.data_ptr()), x.stride(0), k0, _DT[x.dtype], len(layers)
@@ -241,6 +251,12 @@ def chain(x, layers, *, rowmax=False, want_bits=True):
         last = l == len(layers) - 1
         if last and rowmax:
             outs.append(None); bits.append(None)
+            continue
+        if last and last_f32:
+            o = torch.empty((rows, n), dtype=torch.float32, device=dev)
+            a.out_f32, a.n_f32 = C.c_void_p(o.data_ptr()), n
+            L.n = (n + 63) // 64 * 64
+            outs.append(o); bits.append(None)
             continue
         o = torch.empty((rows, n), dtype=x.dtype, device=dev)
         L.out, L.ld_out = C.c_void_p(o.data_ptr()), n

@@ -120,6 +120,8 @@ int pcadv_linear(const pcadv_linear_args* a, void* stream);
  * layer multiplies the tile straight out of shared memory.  With `rowmax_key` the LAST layer stores
  * no output; its pre-activation maximum over the channels goes to rowmax_key[r] (packed key, see
  * pcadv_linear / pcadv_max_finalize) -- torch.max over channels at models/discriminator.py:71.
+ * With `out_f32` the last layer's rows are stored as fp32 instead (fc4's logits, models/pointnet.py:314).
+ * Chains whose widest stored output is 256 run one tile at a time (one shared-memory tile).
  */
 #define PCADV_CHAIN_MAX_LAYERS 4
 typedef struct pcadv_chain_layer {
@@ -144,6 +146,8 @@ typedef struct pcadv_chain_args {
   int32_t num_layers;         /* 2 .. PCADV_CHAIN_MAX_LAYERS */
   pcadv_chain_layer layer[PCADV_CHAIN_MAX_LAYERS];
   unsigned long long* rowmax_key;   /* [rows] or NULL */
+  float* out_f32;             /* or: the last layer's rows as fp32 [rows, n_f32] (contiguous, n_f32 <= 64; the */
+  int32_t n_f32;              /*   layer's n is 64 and its weight has n_f32 rows) -- the segmentation logits   */
 } pcadv_chain_args;
 
 int pcadv_chain(const pcadv_chain_args* a, void* stream);

@@ -173,7 +173,8 @@ def test_tc_wgrad_cta_pair(dtype, rows, ks, rpg):
 
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("rows,widths,rowmax", [(1000, [64, 128, 128, 128], False), (4133, [64, 64, 64, 64, 128], True),
-                                                (129, [256, 128, 64], False), (40000, [128, 128, 128, 64, 64], False)])
+                                                (129, [256, 128, 64], False), (40000, [128, 128, 128, 64, 64], False),
+                                                (5000, [128, 256, 256], False), (4133, [64, 256, 128, 128], True)])
 def test_tc_chain(dtype, rows, widths, rowmax):
     """pcadv_chain (layers multiplied out of shared memory) against the same layers run one by one
     through pcadv_linear: identical stored activations, sign bits and row-max."""
@@ -183,8 +184,7 @@ def test_tc_chain(dtype, rows, widths, rowmax):
         w = _rand((widths[l + 1], widths[l]), 62 + l, dtype, 1.5 / widths[l] ** 0.5)
         b = _rand((widths[l + 1],), 70 + l, torch.float32, 0.1)
         layers.append((w, b, ACT_RELU, 0.0))
-    assert ops.chain_eligible(x, widths)
-    assert not ops.chain_eligible(x, [widths[0], 256, 256])        # two 256-wide tiles do not fit
+    assert ops.chain_eligible(x, widths, allow_serial=True)
     outs, bits, rkey = ops.chain(x, layers, rowmax=rowmax)
     cur = x
     for l, (w, b, act, slope) in enumerate(layers):
@@ -195,6 +195,35 @@ def test_tc_chain(dtype, rows, widths, rowmax):
             v2, i2 = ops.max_finalize(rk, ACT_RELU)
             assert torch.equal(v1, v2) and torch.equal(i1, i2)
             assert outs[l] is None
+            break
+        bt = ops.new_bits(rows, widths[l + 1], DEV)
+        ref, _, _ = ops.linear([cur], w, bias=b, act=act, out_dtype=dtype, engine=ENGINE_TC, bits_out=bt)
+        assert torch.equal(outs[l], ref), l
+        assert torch.equal(bits[l], bt), l
+        cur = ref
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows", [4096, 4133, 129])
+def test_tc_chain_wide_tail_with_fp32_logits(dtype, rows):
+    """The head tail fc2 -> fc3 -> fc4 (256 -> 256 -> 128 -> 50 fp32) as one chained launch (one tile
+    in flight, both epilogue halves split its steps) against the layers run one by one."""
+    widths = [256, 256, 128, 50]
+    x = _rand((rows, 256), 81, dtype).relu_()
+    layers = []
+    for l in range(3):
+        w = _rand((widths[l + 1], widths[l]), 82 + l, dtype, 1.5 / widths[l] ** 0.5)
+        b = _rand((widths[l + 1],), 90 + l, torch.float32, 0.1)
+        layers.append((w, b, ACT_RELU if l < 2 else ACT_NONE, 0.0))
+    assert ops.chain_eligible(x, [256, 256, 128, 64], last_f32=True, allow_serial=True)
+    assert not ops.chain_eligible(x, [256, 256, 128, 64], last_f32=True)     # the models skip the serial mode
+    outs, bits, _ = ops.chain(x, layers, last_f32=True)
+    cur = x
+    for l, (w, b, act, slope) in enumerate(layers):
+        if l == 2:
+            ref, _, _ = ops.linear([cur], w, bias=b, out_dtype=torch.float32, engine=ENGINE_TC)
+            assert outs[l].dtype == torch.float32 and tuple(outs[l].shape) == (rows, 50)
+            assert torch.equal(outs[l], ref)
             break
         bt = ops.new_bits(rows, widths[l + 1], DEV)
         ref, _, _ = ops.linear([cur], w, bias=b, act=act, out_dtype=dtype, engine=ENGINE_TC, bits_out=bt)
