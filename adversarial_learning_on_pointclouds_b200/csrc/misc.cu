@@ -317,18 +317,22 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
   const int g = static_cast<int>(wid / segs);
   const int seg = static_cast<int>(wid - static_cast<int64_t>(g) * segs);
   const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
-  const int cnt = ws[N - 1];
   const int* list = ws + N;
   const float* dzv = reinterpret_cast<const float*>(ws + N + a.n);
-  const int* rowl = ws + N + 2 * a.n;
-  int q = seg * kSegEntries;
-  const int seg_end = q + kSegEntries < cnt ? q + kSegEntries : cnt;
-  if (q >= seg_end) return;
-  if (q > 0) {                         // skip the tail of a run that started in an earlier segment
-    const int prev = rowl[q - 1];
-    while (q < seg_end && rowl[q] == prev) ++q;
-    if (q >= seg_end) return;
-  }
+  const int* rowl = ws + N + 2 * a.n;            // -1 beyond the cloud's last entry
+  // one round trip for the segment's rows and its left neighbour: lanes 0..7 the entries, lane 8
+  // the entry before the segment; a run starts where the row differs from the entry before it
+  const int q0 = seg * kSegEntries;
+  int myrow = -1;
+  if (lane < kSegEntries) myrow = q0 + lane < a.n ? rowl[q0 + lane] : -1;
+  else if (lane == kSegEntries) myrow = q0 > 0 ? rowl[q0 - 1] : -2;
+  const int left = __shfl_sync(0xffffffffu, myrow, lane == 0 ? kSegEntries : (lane - 1) & 31);
+  const unsigned valid = __ballot_sync(0xffffffffu, lane < kSegEntries && myrow >= 0);
+  const unsigned starts = __ballot_sync(0xffffffffu, lane < kSegEntries && myrow >= 0 && myrow != left);
+  if (starts == 0u) return;                      // nothing starts here (or the segment is empty)
+  int q = q0 + __ffs(starts) - 1;
+  const int seg_end = q0 + __popc(valid);        // valid entries are a prefix of the segment
+  const int cnt = a.n;                           // windows below stop at row -1
   const int nvec = a.k >> 3;
   const uint4* wbase = reinterpret_cast<const uint4*>(a.w);
   const int64_t ldw4 = a.ldw >> 3;
@@ -355,7 +359,10 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
       const int mq = q + lane;
       int mrow = -1, mc = 0;
       float mdz = 0.f;
-      if (mq < cnt) { mrow = rowl[mq]; mc = list[mq]; mdz = dzv[mc]; }
+      if (mq < cnt) {
+        mrow = rowl[mq];
+        if (mrow >= 0) { mc = list[mq]; mdz = dzv[mc]; }
+      }
       const unsigned same = __ballot_sync(0xffffffffu, mrow == row);
       const int len = same == 0xffffffffu ? 32 : __ffs(~same) - 1;
       more = len == 32;
