@@ -120,6 +120,10 @@ SYMBOLS = {
     "pcadv_ortho_reg": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcadv_ortho_reg_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
+    "pcadv_part_counts": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcadv_part_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcadv_transpose": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pcadv_version": (C.c_int, []),

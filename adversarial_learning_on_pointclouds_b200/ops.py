@@ -578,6 +578,61 @@ def ortho_reg_bwd(diff, trans, norms, dloss):
     return dT
 
 
+def part_counts(labels, logits=None, pred=None, want_pred=False):
+    """Per-cloud part statistics: see ``pcadv_part_counts``.
+
+    labels: int64 [B, N].  Give either ``logits`` -- a [B, N, C] fp32 tensor with unit stride on C and
+    contiguous points (the storage behind the generator's B x C x N view) -- or ``pred`` int64 [B, N].
+    Returns (counts int32 [B, 3, C] = inter / pred / gt, correct int32 [B], pred int64 [B, N] | None);
+    with ``pred`` given, C is 64 (every label value the kernel supports)."""
+    if (logits is None) == (pred is None):
+        raise ValueError("give either logits or pred")
+    if labels.dtype != torch.int64 or not labels.is_cuda or labels.dim() != 2:
+        raise ValueError("labels must be an int64 CUDA tensor [B, N]")
+    labels = labels.contiguous()
+    B, N = labels.shape
+    if logits is not None:
+        if (logits.dtype != torch.float32 or not logits.is_cuda or logits.dim() != 3
+                or tuple(logits.shape[:2]) != (B, N)):
+            raise ValueError("logits must be an fp32 CUDA tensor [B, N, C] matching labels")
+        Cn = logits.shape[2]
+        if B * N > 0 and (logits.stride(2) != 1 or logits.stride(0) != N * logits.stride(1)):
+            raise ValueError("logits need unit stride on C and evenly strided points, got %s" % (logits.stride(),))
+        ld = logits.stride(1) if N > 1 or B > 1 else Cn
+        lp, pp = _ptr(logits), _ptr(None)
+    else:
+        if pred.dtype != torch.int64 or not pred.is_cuda or tuple(pred.shape) != (B, N):
+            raise ValueError("pred must be an int64 CUDA tensor [B, N]")
+        pred = pred.contiguous()
+        Cn, ld = 64, 0
+        lp, pp = _ptr(None), _ptr(pred)
+    counts = torch.zeros((B, 3, Cn), dtype=torch.int32, device=labels.device)
+    correct = torch.zeros((B,), dtype=torch.int32, device=labels.device)
+    out = torch.empty((B, N), dtype=torch.int64, device=labels.device) if want_pred else None
+    if B * N > 0:
+        _call("part_counts", _lib.lib().pcadv_part_counts, lp, ld, pp, _ptr(labels), B, N, Cn, _ptr(counts),
+              _ptr(correct), _ptr(out), _stream())
+    return counts, correct, out
+
+
+def part_iou(counts, onehot, part_begin):
+    """(iou float64 [B], category int32 [B]) from ``part_counts`` counters: see ``pcadv_part_iou``.
+    onehot: fp32 [B, ncat] (unit column stride); part_begin: int32 device tensor [ncat + 1]."""
+    B, _, Cn = counts.shape
+    if onehot.dtype != torch.float32 or onehot.dim() != 2 or onehot.shape[0] != B or (
+            onehot.shape[1] > 1 and onehot.stride(1) != 1):
+        raise ValueError("onehot must be fp32 [B, ncat] with unit column stride")
+    ncat = onehot.shape[1]
+    if part_begin.dtype != torch.int32 or part_begin.numel() != ncat + 1 or not part_begin.is_contiguous():
+        raise ValueError("part_begin must be a contiguous int32 tensor of ncat + 1 entries")
+    iou = torch.empty((B,), dtype=torch.float64, device=counts.device)
+    cat = torch.empty((B,), dtype=torch.int32, device=counts.device)
+    if B > 0:
+        _call("part_iou", _lib.lib().pcadv_part_iou, _ptr(counts.contiguous()), _ptr(onehot),
+              onehot.stride(0) if B > 1 else ncat, ncat, _ptr(part_begin), B, Cn, _ptr(iou), _ptr(cat), _stream())
+    return iou, cat
+
+
 def transpose(src, out_dtype=None):
     """dst[c, r] = src[r, c] (weight matrices only)."""
     p, ld, dt = _mat(src)
@@ -591,5 +646,5 @@ def transpose(src, out_dtype=None):
 
 __all__ = ["KernelTimer", "Precision", "set_default_precision", "default_precision", "linear", "wgrad",
            "max_finalize", "maxpool_bwd", "rowmax_bwd", "amax_scale", "convert", "transpose",
-           "softmax_head", "logsoftmax_bwd", "HEAD_CE", "HEAD_LSM",
+           "softmax_head", "logsoftmax_bwd", "HEAD_CE", "HEAD_LSM", "part_counts", "part_iou",
            "ACT_NONE", "ACT_RELU", "ACT_LEAKY", "ENGINE_SIMT", "ENGINE_TC"]

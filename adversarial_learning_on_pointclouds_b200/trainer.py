@@ -263,3 +263,59 @@ class GraphedAdversarialSegStep:
         self._slot ^= 1
         self._draw_labels(self._slot)                  # next iteration's labels, under the GPU's shadow
         return self.losses
+
+
+def run_testing_seg(dataloader, dataset, model, criterion, logger, test_iter, writer, args):
+    """The evaluation pass of the reference (``run_testing_seg``, utils/trainer.py:71-143) with the
+    argmax, accuracy count and per-cloud part IoU on the device (``utils.metric.part_iou_from_logits``).
+
+    The reference synchronises four times per batch (``.cpu()`` of the predictions, labels and
+    one-hots, ``loss.item()``); here every batch only enqueues work and the B doubles / counters per
+    batch are read back once after the loop.  Same return value: (accuracy, loss, mean per-category
+    IoU, mean per-cloud IoU), the means taken in float64 on the host exactly as :119-122 does
+    (``np.mean`` of an empty category is nan there as well).  ``logger`` / ``writer`` may be None."""
+    import numpy as np
+    from .utils.metric import object_names, part_iou_from_logits
+
+    model.eval()
+    ious, cats, corrects, losses = [], [], [], []
+    for pts, cls, seg in dataloader:
+        pts = pts.float().to(args.device)                                    # :91-94
+        cls = cls.to(args.device)
+        seg = seg.long().to(args.device)
+        with torch.set_grad_enabled(False):                                  # :96-98
+            pred, _ = model(pts, cls)
+            losses.append(criterion(pred, seg).detach().double())
+            iou, correct, cat = part_iou_from_logits(pred, seg, cls)
+        ious.append(iou)
+        cats.append(cat)
+        corrects.append(correct.sum())
+    if not ious:
+        raise ValueError("run_testing_seg: empty dataloader")
+    iou = torch.cat(ious).cpu().numpy()
+    cat = torch.cat(cats).cpu().numpy()
+    batch_correct = torch.stack(corrects).cpu().numpy()
+    batch_loss = torch.stack(losses).cpu().numpy()
+
+    total_accuracy = 0.0
+    total_loss = 0.0
+    for accu, loss in zip(batch_correct, batch_loss):                        # :101-103
+        total_accuracy += accu / float(args.input_pts)
+        total_loss += float(loss)
+    shape_ious = [[] for _ in object_names]                                  # :86-88, :108-110
+    for b in range(iou.shape[0]):
+        shape_ious[int(cat[b])].append(iou[b])
+    cat_per_iou = [np.mean(i) for i in shape_ious]                           # :119-122
+    all_iou = [i for s in shape_ious for i in s]
+    mean_cat_mious = np.mean(cat_per_iou)
+    mean_all_mious = np.mean(all_iou)
+    n = float(len(dataset))
+    if logger is not None:
+        logger.info("Test accuracy: {:.4f}\tloss: {:.3f}\tcat_iou: {:.4f}\tall_iou: {:.4f}".format(
+            total_accuracy / n, total_loss / n, mean_cat_mious, mean_all_mious))
+    if getattr(args, "tensorboard", False) and writer is not None:           # :133-141
+        writer.add_scalar('Loss/test_cls', total_loss / n, test_iter)
+        writer.add_scalar('Accuracy/test', total_accuracy / n, test_iter)
+        writer.add_scalar('IoU/test_cat_iou', mean_cat_mious, test_iter)
+        writer.add_scalar('IoU/test_all_iou', mean_all_mious, test_iter)
+    return total_accuracy / n, total_loss / n, mean_cat_mious, mean_all_mious

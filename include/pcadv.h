@@ -333,6 +333,30 @@ int pcadv_ortho_reg(const float* T, int32_t groups, int32_t d, float* diff, floa
 int pcadv_ortho_reg_bwd(const float* diff, const float* T, const float* norms, const float* dloss,
                         int32_t groups, int32_t d, float* dT, void* stream);
 
+/*
+ * Part-IoU evaluation on the device: utils/metric.py:20-39 (get_iou /
+ * batch_get_iou) and the argmax + accuracy count of run_testing_seg, utils/trainer.py:100-110,
+ * which the reference computes with numpy on the host from a copy of every prediction.
+ *
+ * pcadv_part_counts: for each cloud g of N points, pred = argmax over the C columns of
+ *   logits[p, :] (fp32, row stride ld; the first maximum, as pred.max(1)[1]) -- or pred_in[p] when
+ *   logits is NULL (exactly one of the two is given) -- then, with gt = labels[p] (int64),
+ *     counts[g, 0, l] += #(pred == l && gt == l)   counts[g, 1, l] += #(pred == l)
+ *     counts[g, 2, l] += #(gt == l)                correct[g]      += #(pred == gt)
+ *   counts: int32 [groups, 3, C], correct: int32 [groups]; the caller zero-fills both.
+ *   pred_out (nullable): int64 [groups * N] receives the predictions.  C <= 64, groups <= 65535.
+ * pcadv_part_iou: cat[g] = argmax of onehot[g, 0..ncat) (first maximum, np.argmax), parts
+ *   l in [part_begin[cat], part_begin[cat + 1]) (device int32 [ncat + 1]; seg_classes of
+ *   utils/metric.py:5), iou[g] = mean_l (pred and gt both empty ? 1 : inter / union) in float64,
+ *   summed in index order as np.mean does for fewer than 8 terms.
+ */
+int pcadv_part_counts(const float* logits, int64_t ld, const int64_t* pred_in, const int64_t* labels,
+                      int32_t groups, int64_t N, int32_t C, int32_t* counts, int32_t* correct,
+                      int64_t* pred_out, void* stream);
+int pcadv_part_iou(const int32_t* counts, const float* onehot, int64_t ld_onehot, int32_t ncat,
+                   const int32_t* part_begin, int32_t groups, int32_t C, double* iou, int32_t* cat,
+                   void* stream);
+
 /* dst[c, r] = src[r, c] with conversion: builds the [k, n] copy of a weight
  * matrix that dgrad consumes. */
 int pcadv_transpose(const void* src, int32_t src_dtype, int64_t ld_src, int32_t rows, int32_t cols,

@@ -16,13 +16,16 @@ from . import pointnet_oracle as P
 from . import discriminator_oracle as D
 
 
-def make_D_label(shape, value, random, generator=None):
+def make_D_label(shape, value, random, generator=None, device=None):
     """utils/utils.py:22-31: constant 0/1 target, or U(0, 0.305) for value 0 and
-    U(0.7, 1.05) for value 1, drawn on the CPU (default generator there)."""
+    U(0.7, 1.05) for value 1, drawn on the CPU (default generator there) and then
+    moved to ``device`` (:31)."""
     if random:
         lo, hi = (0.0, 0.305) if value == 0 else (0.7, 1.05)
-        return torch.empty(shape, dtype=torch.float32).uniform_(lo, hi, generator=generator)
-    return torch.full(shape, float(value), dtype=torch.float32)
+        lab = torch.empty(shape, dtype=torch.float32).uniform_(lo, hi, generator=generator)
+    else:
+        lab = torch.full(shape, float(value), dtype=torch.float32)
+    return lab if device is None else lab.to(device)
 
 
 def _set_requires_grad(params, flag):
@@ -61,17 +64,17 @@ def adversarial_seg_step(g_params, d_params, batch_gt, batch_nogt, disc="pointwi
     pred_nogt, _ = P.pointnet_seg_forward(g_params, pts_nogt, cls_nogt)       # :913
     pred_nogt_softmax = F.log_softmax(pred_nogt, dim=1)                       # :914
     D_out = run_D(pred_nogt_softmax)                                          # :916
-    l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False))
+    l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False, device=D_out.device))
     (lambda_seg * l_seg + lambda_adv * l_adv).backward()                      # :927-929
 
     # ---- train D (:931-963)
     _set_requires_grad(d_params, True)
     D_out = run_D(pred_gt_softmax.detach())                                   # :936-938
-    lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator)
+    lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator, D_out.device)
     l_D_gt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5             # :946-947
     l_D_gt.backward()
     D_out = run_D(pred_nogt_softmax.detach())                                 # :951-953
-    lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator)
+    lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator, D_out.device)
     l_D_nogt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5           # :961-962
     l_D_nogt.backward()
     return dict(l_seg=l_seg.item(), l_adv=l_adv.item(), l_D_gt=l_D_gt.item(),
@@ -93,15 +96,15 @@ def adversarial_cls_step(g_params, d_params, batch_gt, batch_nogt, lambda_cls=1.
     pred_nogt, _, _ = P.pointnet_cls_forward(g_params, pts_nogt, training=training)  # :490
     pred_nogt_ls = F.log_softmax(pred_nogt, dim=1)                            # :492
     D_out = D.deepconv_disc_forward(d_params, pred_nogt_ls)                   # :499
-    l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False))
+    l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False, device=D_out.device))
     (lambda_cls * l_cls + lambda_adv * l_adv).backward()
     _set_requires_grad(d_params, True)
     D_out = D.deepconv_disc_forward(d_params, pred_gt_ls.detach())            # :530
-    lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator)
+    lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator, D_out.device)
     l_D_gt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5
     l_D_gt.backward()
     D_out = D.deepconv_disc_forward(d_params, pred_nogt_ls.detach())          # :546
-    lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator)
+    lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator, D_out.device)
     l_D_nogt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5
     l_D_nogt.backward()
     return dict(l_cls=l_cls.item(), l_adv=l_adv.item(), l_D_gt=l_D_gt.item(),
