@@ -75,6 +75,22 @@ def cases(P, N):
     lin("dz1", [128, 256], 64, mask=True, bias=False)
     lin("disc4max", [64], 128, rowmax=True, want_out=False)
 
+    # chained narrow layers (pcadv_chain): the generator trunk conv2 -> conv4 and the head tail
+    def chain(name, k0, widths, last_f32=False):
+        x = r16((P, k0))
+        layers, k = [], k0
+        for i, n in enumerate(widths):
+            act = ACT_NONE if (last_f32 and i == len(widths) - 1) else ACT_RELU
+            layers.append((r16((n, k), 0.05), torch.randn(n, device=DEV), act, 0.0))
+            k = n
+        nb = P * 2 * k0 + sum(P * (4 * n if (last_f32 and i == len(widths) - 1) else 2 * n + n // 8)
+                              for i, n in enumerate(widths))
+        fl = 2.0 * P * sum(a * b for a, b in zip([k0] + widths[:-1], widths))
+        c[name] = (lambda: ops.chain(x, layers, last_f32=last_f32), nb, fl)
+
+    chain("chain_trunk", 64, [128, 128, 128])
+    chain("chain_tail", 256, [128, 50], last_f32=True)
+
     def wg(name, n, ks, dbias=True):
         dz = r16((P, n))
         segs = [r16((P, k)) for k in ks]
@@ -151,7 +167,7 @@ def main():
     cs = cases(args.points, args.n)
     print("%-12s %9s %9s %9s" % ("op", "ms", "GB/s", "TFLOP/s"))
     for name, (fn, nbytes, flops) in cs.items():
-        if args.only and name != args.only:
+        if args.only and name not in args.only.split(","):
             continue
         fn()
         torch.cuda.synchronize()
