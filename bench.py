@@ -335,6 +335,8 @@ def run_cuda(args):
                     "traffic": 1.0898e9 if (Bg + Bn) // 2 * N == (1 << 20) else None,
                     "traffic_unit": "bytes per launch (ncu --set full, round 1)",
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "peak_burst": peaks.get("bf16_burst"),
+                    "frac_of_burst": (achieved / peaks["bf16_burst"]) if peaks.get("bf16_burst") else None,
                     "launch_ms": per_launch_s * 1e3, "share_of_step": tot_ms / ms_eager,
                     "timing": "CUDA events around the launch on the launching stream, in an eager "
                               "pass of the same step (%d steps, %.2f ms/step eager)" % (args.steps,
