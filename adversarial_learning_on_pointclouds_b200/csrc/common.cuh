@@ -64,6 +64,16 @@ __device__ __forceinline__ void st_from_float(void* p, int64_t i, int dtype, flo
 
 // two floats -> one packed 16-bit pair (lo in the low half); fp16 saturates to +-65504 instead
 // of producing inf (one F2FP.SATFINITE instruction)
+// ReLU on a packed pair: max(x, +0) per half.  Same bits as packing fmaxf(x, 0.f) for every finite
+// or infinite x: rounding and saturation are monotone and keep the sign, and -0 becomes +0 either way.
+template <bool kBf16>
+__device__ __forceinline__ uint32_t relu_packed(uint32_t pk) {
+  uint32_t r;
+  if (kBf16) asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(pk), "r"(0u));
+  else asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(pk), "r"(0u));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

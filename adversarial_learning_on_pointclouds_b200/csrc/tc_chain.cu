@@ -293,10 +293,8 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                   asm volatile("st.shared.f32 [%0], %1;" ::"r"(crow + j * 4), "f"(v[j]) : "memory");
               continue;
             }
-            if (act == PCADV_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (act == PCADV_ACT_LEAKY) {
+            // ReLU: on the packed halves below
+            if (act == PCADV_ACT_LEAKY) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
             }
@@ -304,6 +302,10 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               pk[j] = kBf16 ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
+            if (act == PCADV_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = relu_packed<kBf16>(pk[j]);
+            }
             if (want_bits) {
               uint32_t w = 0u;
 #pragma unroll

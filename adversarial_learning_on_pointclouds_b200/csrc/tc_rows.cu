@@ -389,10 +389,8 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
             }
             continue;
           }
-          if (kAct == PCADV_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (kAct == PCADV_ACT_LEAKY) {
+          // ReLU is applied to the packed halves below (one HMNMX2 per pair instead of two FMNMX)
+          if (kAct == PCADV_ACT_LEAKY) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
           }
@@ -406,6 +404,10 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             pk[j] = kOut == PCADV_F16 ? pack_f16x2_sat(v[2 * j], v[2 * j + 1]) : pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (kAct == PCADV_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = relu_packed<kOut == PCADV_BF16>(pk[j]);
+          }
           if (want_bits) {
             uint32_t w = 0u;
 #pragma unroll
