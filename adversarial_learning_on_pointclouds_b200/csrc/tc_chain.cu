@@ -58,7 +58,17 @@ struct ChainParams {
   int serial;                                 // one tile in flight, both halves split its steps (wide chains)
   int nstages, stage_bytes, h_bytes;
   int bf16;
+  // debugging aid (pcadv_debug_chain_trace): clock64 stamps of CTA 0, [warp 0..9][slot 0..kTraceSlots)
+  long long* trace;
 };
+constexpr int kTraceSlots = 256;
+#define CHAIN_STAMP(slot_expr)                                                         \
+  do {                                                                                 \
+    if (tracing && lane == 0) {                                                        \
+      const int s_ = (slot_expr);                                                      \
+      if (s_ < kTraceSlots) p.trace[warp * kTraceSlots + s_] = clock64();              \
+    }                                                                                  \
+  } while (0)
 
 struct ChainSmem {
   uint8_t* stages;
@@ -122,6 +132,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int NL = p.num_layers;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.x);
@@ -189,7 +200,10 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           const int chunks = p.k[l] >> 6;
           for (int h = 0; h < tiles_in_flight && i0 + h < my_tiles; ++h) {
             // H[h] holds the previous layer's output (l > 0) and the accumulator has been drained
+            const int tslot = static_cast<int>(((i0 / tiles_in_flight) * NL + l) * 2 + h) * 3;
+            CHAIN_STAMP(tslot);
             mbar_wait_backoff(&st->in_ready[h], ready_par[h] ^ 1);
+            CHAIN_STAMP(tslot + 1);
             ready_par[h] ^= 1;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(h * kMaxTileN);
@@ -204,6 +218,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
             umma_commit(&st->acc_full[h]);
+            CHAIN_STAMP(tslot + 2);
           }
         }
       }
@@ -237,7 +252,10 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int act = p.act[l];
         const float slope = p.slope[l];
         const uint32_t bias_a = smem_u32(L.bias + l * kMaxTileN);
+        const int eslot = static_cast<int>((i / tiles_in_flight) * NL + l) * 6;
+        CHAIN_STAMP(eslot);
         mbar_wait(&st->acc_full[buf], full_par);
+        CHAIN_STAMP(eslot + 1);
         full_par ^= 1;
         tc_fence_after();
         // H[half] was the A operand of the MMAs that just completed; the TMA stores issued from it
@@ -258,6 +276,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           tmem_ld32_issue(taddr0 + step * 64 + 32, raw[1]);
           tmem_ld32_wait(raw[0]);
           tmem_ld32_wait(raw[1]);
+          if (step == 0) CHAIN_STAMP(eslot + 2);
           uint32_t obits[2] = {0u, 0u};
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -318,6 +337,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           }
           if (rowmax || f32out) continue;
           if (want_bits) c_sts64(bits_s + (lane * kChainBitsWords + 2 * step) * 4, obits[0], obits[1]);
+          if (step == 0) CHAIN_STAMP(eslot + 3);
           fence_proxy_async();                             // slab visible to the TMA store and the next MMA
           __syncwarp();
           if (p.has_out[l] && lane == 0) {
@@ -375,9 +395,11 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           __syncwarp();
         }
         // H[half] = this layer's output, accumulator drained: the next MMA of this half may go
+        CHAIN_STAMP(eslot + 4);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&st->in_ready[buf]);
+        CHAIN_STAMP(eslot + 5);
       }
     }
     if (lane == 0) bulk_wait_group<0>();
@@ -395,6 +417,11 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 
 using namespace pcadv;
 
+static long long* g_chain_trace = nullptr;
+// Debugging aid, not part of the ABI in include/pcadv.h: the next pcadv_chain launches record
+// clock64 stamps of CTA 0 into `buf` ([10 warps][256 slots] int64, device memory); NULL switches off.
+extern "C" void pcadv_debug_chain_trace(long long* buf) { g_chain_trace = buf; }
+
 extern "C" int pcadv_chain(const pcadv_chain_args* a, void* stream) {
   using namespace tc;
   PCADV_CHECK_ARG(a && a->num_layers >= 2 && a->num_layers <= kChainMaxLayers, "pcadv_chain: 2..4 layers");
@@ -409,6 +436,7 @@ extern "C" int pcadv_chain(const pcadv_chain_args* a, void* stream) {
   p.bf16 = dt == PCADV_BF16 ? 1 : 0;
   p.rowmax_key = a->rowmax_key;
   p.out_f32 = a->out_f32; p.n_f32 = a->n_f32;
+  p.trace = g_chain_trace;
   PCADV_CHECK_ARG(!(a->rowmax_key && a->out_f32), "pcadv_chain: rowmax_key and out_f32 are exclusive");
   PCADV_CHECK_ARG(!a->out_f32 || (a->n_f32 >= 1 && a->n_f32 <= 64 && a->layer[a->num_layers - 1].n == 64 &&
                                   (reinterpret_cast<uintptr_t>(a->out_f32) & 3) == 0),
