@@ -23,6 +23,19 @@ def _prec(module):
     return getattr(module, "precision", None) or ops.default_precision()
 
 
+def _holders(module, *spec):
+    """Register the reference's parameter holders in the reference's creation order (the order
+    fixes which random numbers initialise which tensor): ``(name, cin, cout)`` makes the
+    ``nn.Conv1d(cin, cout, 1)`` child ``name``; names starting with "fc" make ``nn.Linear``."""
+    for name, cin, cout in spec:
+        child = nn.Linear(cin, cout) if name.startswith("fc") else nn.Conv1d(cin, cout, 1)
+        setattr(module, name, child)
+
+
+def _leaky_holder(inplace=True):
+    return nn.LeakyReLU(negative_slope=0.2, inplace=inplace)
+
+
 def _rows(x_bcn):
     """The B x C x N map is handed to PointMLPFunction as is: it reads channel-major
     memory (torch softmax output) and transposed views of point-major storage (the
@@ -41,11 +54,8 @@ class ConvDiscNet(nn.Module):
     """models/discriminator.py:10-28.  x: B x N x C -> B x N."""
 
     def __init__(self, input_dim):
-        super(ConvDiscNet, self).__init__()
-        self.conv1 = torch.nn.Conv1d(input_dim, 256, 1)
-        self.conv2 = torch.nn.Conv1d(256, 64, 1)
-        self.conv3 = torch.nn.Conv1d(64, 16, 1)
-        self.fc = nn.Linear(16, 1)
+        super().__init__()
+        _holders(self, ("conv1", input_dim, 256), ("conv2", 256, 64), ("conv3", 64, 16), ("fc", 16, 1))
         self.relu = nn.ReLU()
 
     def forward(self, x):
@@ -59,14 +69,11 @@ class DeepConvDiscNet(nn.Module):
     """models/discriminator.py:30-51.  x: B x C -> B x output_dim."""
 
     def __init__(self, input_dim, output_dim):
-        super(DeepConvDiscNet, self).__init__()
-        self.conv1 = torch.nn.Conv1d(input_dim, 512, 1)
-        self.conv2 = torch.nn.Conv1d(512, 256, 1)
-        self.conv3 = torch.nn.Conv1d(256, 256, 1)
-        self.conv4 = torch.nn.Conv1d(256, 64, 1)
-        self.conv5 = torch.nn.Conv1d(64, 64, 1)
-        self.fc = nn.Linear(64, output_dim)
-        self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        super().__init__()
+        widths = [input_dim, 512, 256, 256, 64, 64]
+        _holders(self, *[("conv%d" % (i + 1), widths[i], widths[i + 1]) for i in range(5)],
+                 ("fc", 64, output_dim))
+        self.leaky_relu = _leaky_holder()
 
     def forward(self, x):
         return point_mlp(_prec(self), x, [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5,
@@ -77,12 +84,10 @@ class PointwiseDiscNet(nn.Module):
     """models/discriminator.py:53-79.  x: B x C x N -> B x N (max over channels)."""
 
     def __init__(self, input_pts, input_dim):
-        super(PointwiseDiscNet, self).__init__()
+        super().__init__()
         self.input_pts = input_pts
-        self.conv1 = torch.nn.Conv1d(input_dim, 64, 1)
-        self.conv2 = torch.nn.Conv1d(64, 64, 1)
-        self.conv3 = torch.nn.Conv1d(64, 64, 1)
-        self.conv4 = torch.nn.Conv1d(64, 128, 1)
+        widths = [input_dim, 64, 64, 64, 128]
+        _holders(self, *[("conv%d" % (i + 1), widths[i], widths[i + 1]) for i in range(4)])
 
     def forward(self, x):
         rows, B, N, box = _rows(x)
@@ -96,13 +101,11 @@ class BaseDiscNet(nn.Module):
     reference's forward never applies it).  x: B x C x N -> B x output_dim x N."""
 
     def __init__(self, input_pts, input_dim, output_dim):
-        super(BaseDiscNet, self).__init__()
+        super().__init__()
         self.input_pts = input_pts
-        self.conv1 = torch.nn.Conv1d(input_dim, 64, 1)
-        self.conv2 = torch.nn.Conv1d(64, 64, 1)
-        self.conv3 = torch.nn.Conv1d(64, output_dim, 1)
-        self.conv4 = torch.nn.Conv1d(output_dim, output_dim, 1)
-        self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        widths = [input_dim, 64, 64, output_dim, output_dim]
+        _holders(self, *[("conv%d" % (i + 1), widths[i], widths[i + 1]) for i in range(4)])
+        self.leaky_relu = _leaky_holder()
 
     def forward(self, x):
         rows, B, N, box = _rows(x)
@@ -114,12 +117,11 @@ class ShapeDiscNet(nn.Module):
     """models/discriminator.py:100-117.  x: B x C x N -> B x num_shapes."""
 
     def __init__(self, shared_output_dim, num_shapes):
-        super(ShapeDiscNet, self).__init__()
+        super().__init__()
         self.interm_dim = 512
-        self.conv = torch.nn.Conv1d(shared_output_dim, self.interm_dim, 1)
-        self.fc1 = torch.nn.Linear(self.interm_dim, 64)
-        self.fc2 = torch.nn.Linear(64, num_shapes)
-        self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        _holders(self, ("conv", shared_output_dim, self.interm_dim), ("fc1", self.interm_dim, 64),
+                 ("fc2", 64, num_shapes))
+        self.leaky_relu = _leaky_holder()
 
     def forward(self, x):
         rows, B, N, _ = _rows(x)
@@ -132,12 +134,10 @@ class PointDiscNet(nn.Module):
     """models/discriminator.py:119-137.  x: B x C x N -> B x N (max over channels)."""
 
     def __init__(self, shared_output_dim, input_pts):
-        super(PointDiscNet, self).__init__()
+        super().__init__()
         self.input_pts = input_pts
-        self.conv1 = torch.nn.Conv1d(shared_output_dim, 256, 1)
-        self.conv2 = torch.nn.Conv1d(256, 128, 1)
-        self.conv3 = torch.nn.Conv1d(128, 128, 1)
-        self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        _holders(self, ("conv1", shared_output_dim, 256), ("conv2", 256, 128), ("conv3", 128, 128))
+        self.leaky_relu = _leaky_holder()
 
     def forward(self, x):
         rows, B, N, _ = _rows(x)
@@ -151,19 +151,18 @@ class StackDiscNet(nn.Module):
     disc_out B x N x 1)."""
 
     def __init__(self, input_pts, input_dim, num_shapes):
-        super(StackDiscNet, self).__init__()
+        super().__init__()
         self.input_pts = input_pts
-        self.conv1 = torch.nn.Conv1d(input_dim, 64, 1)
-        self.conv2 = torch.nn.Conv1d(64, 64, 1)
-        self.conv3 = torch.nn.Conv1d(64, 64, 1)
-        self.conv4 = torch.nn.Conv1d(64, 128, 1)
-        self.conv5 = torch.nn.Conv1d(1, num_shapes, 1)
-        self.leaky_relu = nn.LeakyReLU(negative_slope=0.2)
+        widths = [input_dim, 64, 64, 64, 128]
+        _holders(self, *[("conv%d" % (i + 1), widths[i], widths[i + 1]) for i in range(4)],
+                 ("conv5", 1, num_shapes))
+        self.leaky_relu = _leaky_holder(inplace=False)
 
     def custom_activation(self, x):
-        x = x.transpose(2, 1)
-        out = torch.logsumexp(x, dim=2, keepdim=True)
-        return out / (out + 1.0)
+        """z / (z + 1) with z = logsumexp over the shape channel (models/discriminator.py:155-159);
+        B x S x N -> B x N x 1."""
+        z = torch.logsumexp(x.transpose(1, 2), dim=2, keepdim=True)
+        return z / (z + 1.0)
 
     def forward(self, x):
         rows, B, N, box = _rows(x)
