@@ -143,6 +143,76 @@ def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, o
     return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
 
 
+def pointnet_cls_step(model, cls_loss, optimizer, batch, args):
+    """One iteration of run_training_pointnet_cls (utils/trainer.py:236-269): PointNetCls forward,
+    ``cls_loss`` + ``lambda_regu`` x feature_transform_regularizer when the model has a feature
+    transform, backward, optimizer step.  ``batch`` = (pts B x N x 3, labels B) on ``args.device``;
+    ``args`` needs ``lambda_cls`` and ``lambda_regu``.  Returns (l_cls, l_regu | None) as device
+    tensors (the reference calls ``.item()`` on both, :256-259)."""
+    from .models.pointnet import feature_transform_regularizer
+    with weight_cache():
+        model.train()
+        optimizer.zero_grad()
+        pts, labels = batch
+        pred, _, high_feat = model(pts)
+        l_cls = cls_loss(pred, labels)
+        l_regu = feature_transform_regularizer(high_feat) if high_feat is not None else None
+        loss = args.lambda_cls * l_cls
+        if l_regu is not None:
+            loss = loss + args.lambda_regu * l_regu
+        loss.backward()
+        optimizer.step()
+    return l_cls.detach(), (l_regu.detach() if l_regu is not None else None)
+
+
+def adversarial_cls_step(model, model_D, gan_loss, cls_loss, optimizer, optimizer_D, batch_gt, batch_nogt,
+                         args, history_pool_gt=None, history_pool_nogt=None, device_labels=False,
+                         label_fn=None):
+    """One iteration of run_training (utils/trainer.py:426-559): the classification counterpart of
+    ``adversarial_seg_step`` -- G = PointNetCls, D = DeepConvDiscNet on ``log_softmax`` of the class
+    logits for BOTH discriminator inputs (:472, :492).  batch_gt = (pts, labels), batch_nogt = pts or
+    (pts,).  Returns (l_cls, l_adv, l_D) as 0-d device tensors."""
+    pool_gt = history_pool_gt or ImagePool(0)
+    pool_nogt = history_pool_nogt or ImagePool(0)
+
+    def label(d_out, value, random):
+        if label_fn is not None:
+            return label_fn(d_out, value, random)
+        if device_labels:
+            return _device_label(d_out, value, random)
+        return make_D_label(input=d_out, value=value, device=args.device, random=random)
+
+    with weight_cache():
+        model.train()
+        model_D.train()
+        optimizer.zero_grad()
+        optimizer_D.zero_grad()
+        for param in model_D.parameters():                                   # :455-456
+            param.requires_grad = False
+        pts, labels = batch_gt
+        pred, _, _ = model(pts)                                              # :468
+        l_cls = cls_loss(pred, labels)
+        pred_gt_ls = F.log_softmax(pred, dim=1)                              # :472
+        pts_nogt = batch_nogt[0] if isinstance(batch_nogt, (tuple, list)) else batch_nogt
+        pred_nogt, _, _ = model(pts_nogt)                                    # :490
+        pred_nogt_ls = F.log_softmax(pred_nogt, dim=1)                       # :492
+        D_out = model_D(pred_nogt_ls)                                        # :499
+        loss_adv = gan_loss(D_out, label(D_out, 1, False))
+        (args.lambda_cls * l_cls + args.lambda_adv * loss_adv).backward()    # :511-521
+
+        for param in model_D.parameters():                                   # :524-525
+            param.requires_grad = True
+        D_out = model_D(pool_gt.query(pred_gt_ls.detach()))                  # :529-531
+        loss_D_gt = gan_loss(D_out, label(D_out, 1, True)) * 0.5
+        loss_D_gt.backward()
+        D_out = model_D(pool_nogt.query(pred_nogt_ls.detach()))              # :545-547
+        loss_D_nogt = gan_loss(D_out, label(D_out, 0, True)) * 0.5
+        loss_D_nogt.backward()
+        optimizer.step()                                                     # :558-559
+        optimizer_D.step()
+    return l_cls.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
+
+
 class GraphedAdversarialSegStep:
     """``adversarial_seg_step`` captured once into a CUDA graph and replayed.
 

@@ -409,6 +409,76 @@ def test_adversarial_step_vs_oracle_step(mode):
         assert rel_err(v.grad, gp[k].grad) < loose, k
 
 
+# ------------------------------------------------------------- classification loop bodies (a15)
+@pytest.mark.parametrize("ft", [False, True])
+@pytest.mark.parametrize("mode", MODES)
+def test_pointnet_cls_step_vs_oracle(mode, ft):
+    """trainer.pointnet_cls_step (utils/trainer.py:236-269) against oracle.steps.pointnet_cls_step:
+    CE + lambda_regu * regulariser, same losses and gradients.  Dropout is switched off on both
+    sides (its random stream cannot be shared between the CPU oracle and the device)."""
+    from adversarial_learning_on_pointclouds_b200.trainer import pointnet_cls_step
+    import argparse
+    torch.manual_seed(3)
+    m = M.PointNetCls(40, ft)
+    randomize_biases([m], 6)
+    gp = steps.leaf_params(m.state_dict())
+    m.to(DEV)
+    m.dropout.p = 0.0
+    for mod in m.modules():
+        mod.precision = Precision(mode)
+    pts, y, _, _ = inputs(4, 300, 21)
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    targs = argparse.Namespace(device=DEV, lambda_cls=1.0, lambda_regu=1e-3)
+    l_cls, l_regu = pointnet_cls_step(m, torch.nn.CrossEntropyLoss(), opt, (pts.to(DEV), y.to(DEV)), targs)
+    ref = steps.pointnet_cls_step(gp, (pts, y), feature_transform=ft, lambda_regu=1e-3)
+    tol = TOL[mode]
+    assert abs(l_cls.item() - ref["l_cls"]) < 10 * tol
+    assert (l_regu is None) == (not ft)
+    if ft:
+        assert abs(l_regu.item() - ref["l_regu"]) < 10 * tol * ref["l_regu"]
+    # un-conditioned: with 4 x 300 points behind a 1024-channel max-pool one arg-max that flips in
+    # the 16-bit forward moves the first layers' gradients by several per cent (DESIGN.md section 5;
+    # the branch-conditioned comparison is test_cls_kat1 / test_seg_matches_oracle)
+    loose = 5e-3 if mode == "fp32" else 0.15
+    for k, v in m.named_parameters():
+        assert rel_err(v.grad, gp[k].grad) < loose, k
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_adversarial_cls_step_vs_oracle(mode):
+    """trainer.adversarial_cls_step (utils/trainer.py:426-559: PointNetCls against DeepConvDiscNet on
+    log_softmax maps) against oracle.steps.adversarial_cls_step."""
+    from adversarial_learning_on_pointclouds_b200.trainer import adversarial_cls_step
+    import argparse
+    torch.manual_seed(4)
+    g = M.PointNetCls(40, False)
+    d = init_net(M.DeepConvDiscNet(40, 1), "cpu", "xavier")
+    randomize_biases([g, d], 8)
+    gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
+    g.to(DEV); d.to(DEV)
+    g.dropout.p = 0.0
+    for mod in list(g.modules()) + list(d.modules()):
+        mod.precision = Precision(mode)
+    pts, y, _, _ = inputs(6, 200, 31)
+    pts2, _, _, _ = inputs(6, 200, 32)
+    opt = torch.optim.SGD(g.parameters(), lr=0.0)
+    optD = torch.optim.SGD(d.parameters(), lr=0.0)
+    targs = argparse.Namespace(device=DEV, lambda_cls=1.0, lambda_adv=0.5)
+    torch.manual_seed(77)
+    l_cls, l_adv, l_D = adversarial_cls_step(g, d, torch.nn.BCEWithLogitsLoss(), torch.nn.CrossEntropyLoss(),
+                                             opt, optD, (pts.to(DEV), y.to(DEV)), pts2.to(DEV), targs)
+    torch.manual_seed(77)
+    ref = steps.adversarial_cls_step(gp, dp, (pts, y), (pts2,), lambda_adv=0.5)
+    tol = TOL[mode]
+    assert abs(l_cls.item() - ref["l_cls"]) < 10 * tol and abs(l_adv.item() - ref["l_adv"]) < 10 * tol
+    assert abs(l_D.item() - (ref["l_D_gt"] + ref["l_D_nogt"])) < 10 * tol
+    loose = 5e-3 if mode == "fp32" else 0.15                                  # un-conditioned, as above
+    for k, v in d.named_parameters():
+        assert rel_err(v.grad, dp[k].grad) < loose, k
+    for k, v in g.named_parameters():
+        assert rel_err(v.grad, gp[k].grad) < loose, k
+
+
 # ------------------------------------------------------------- fused loss heads (SURVEY 8f-1)
 @pytest.mark.parametrize("out_dtype,cols", [(torch.float32, 50), (torch.float16, 64), (torch.bfloat16, 64)])
 @pytest.mark.parametrize("rows", [1, 77, 4096 + 5])
