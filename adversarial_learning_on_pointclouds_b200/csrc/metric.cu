@@ -24,7 +24,9 @@ __global__ void __launch_bounds__(kPcRows) part_counts_kernel(
   extern __shared__ float tile[];                        // [128][pitch], pitch odd -> conflict-free row scans
   __shared__ int hist[3 * kPcMaxC + 1];
   const int t = threadIdx.x, g = blockIdx.y;
-  const int pitch = C | 1;
+  const bool flat8 = logits != nullptr && ld == C && (C & 1) == 0 &&
+                     (reinterpret_cast<uintptr_t>(logits) & 7) == 0;
+  const int pitch = flat8 ? C : (C | 1);
   for (int e = t; e < 3 * kPcMaxC + 1; e += kPcRows) hist[e] = 0;
   const int64_t tiles = (N + kPcRows - 1) / kPcRows;
   for (int64_t tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
@@ -35,7 +37,16 @@ __global__ void __launch_bounds__(kPcRows) part_counts_kernel(
     __syncthreads();                                     // hist zeroed / previous tile scanned
     if (logits != nullptr) {
       const float* src = logits + p0 * ld;
-      if (ld == C) {                                     // contiguous rows: flat coalesced copy
+      if (flat8) {
+        // contiguous rows, 8-byte aligned: the tile is one flat copy, every 8-byte piece in flight
+        // at once (cp.async), unpadded rows (pitch C: a 2-way bank conflict in the scan below)
+        const int pieces = rows * C / 2;
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+        for (int e = t; e < pieces; e += kPcRows)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + e * 8), "l"(src + 2 * e) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else if (ld == C) {                              // contiguous rows: flat coalesced copy
         const int total = rows * C;
         int r = t / C, c = t - r * C;                    // walk (r, c) without a division per element
         const int dr = kPcRows / C, dc = kPcRows - dr * C;

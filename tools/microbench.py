@@ -134,6 +134,14 @@ def cases(P, N):
     c["maxbwd_rows"] = (lambda: ops.maxpool_bwd(dg6, g6, idx6, x5, w6, N, act=ACT_RELU, dz_inout=dz5,
                                                 prev_act=ACT_RELU), B * 2048 * 1024, 2.0 * B * 2048 * 512)
 
+    # evaluation: argmax over 50 logits + per-cloud part counts + IoU (utils/metric.py on the device)
+    from adversarial_learning_on_pointclouds_b200.utils import metric as DM
+    lg = torch.randn((B, N, 50), device=DEV)
+    sg = torch.randint(0, 50, (B, N), device=DEV)
+    oh = torch.zeros((B, 16), device=DEV)
+    oh[torch.arange(B), torch.randint(0, 16, (B,), device=DEV)] = 1.0
+    c["part_iou"] = (lambda: DM.part_iou_from_logits(lg, sg, oh), P * (200 + 8), 0.0)
+
     x50 = torch.randn((P, 50), device=DEV)
     w50 = torch.randn((64, 50), device=DEV) * 0.1
     c["disc1_simt"] = (lambda: ops.linear([x50], w50, bias=torch.zeros(64, device=DEV), act=ACT_RELU,
