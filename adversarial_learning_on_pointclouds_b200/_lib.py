@@ -66,7 +66,7 @@ class HeadArgs(C.Structure):
         ("probs", C.c_void_p), ("ld_probs", C.c_int64), ("probs_dtype", C.c_int32),
         ("probs_cols", C.c_int32),
         ("dz", C.c_void_p), ("ld_dz", C.c_int64), ("dz_dtype", C.c_int32), ("dz_cols", C.c_int32),
-        ("dz_gain", C.c_float), ("loss_sum", C.c_void_p),
+        ("dz_gain", C.c_float), ("loss_sum", C.c_void_p), ("valid_count", C.c_void_p),
     ]
 
 

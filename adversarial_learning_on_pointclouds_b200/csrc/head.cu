@@ -27,7 +27,7 @@ __device__ __forceinline__ void flush_tile16(const uint32_t* stage, void* dst, i
 // shared memory (odd row stride: conflict-free row-per-thread reads); then thread = row.
 __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args a) {
   extern __shared__ float sm[];
-  __shared__ float red[8];
+  __shared__ float red[16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
   const int ldt = n | 1;                                   // odd stride
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
   const bool packed_d = a.dz && a.dz_dtype != PCADV_F32 && a.dz_cols == 64 && a.ld_dz == 64 &&
                         (reinterpret_cast<uintptr_t>(a.dz) & 15) == 0 && n <= 64;
   const int64_t nblk = (a.rows + 31) / 32;
-  float loss = 0.f;
+  float loss = 0.f, valid = 0.f;
   for (int64_t blk = static_cast<int64_t>(blockIdx.x) * 8 + warp; blk < nblk;
        blk += static_cast<int64_t>(gridDim.x) * 8) {
     const int64_t row0 = blk * 32;
@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
       float m = t[0];
       for (int c = 1; c < n; ++c) m = fmaxf(m, t[c]);
       float s = 0.f;
-      for (int c = 0; c < n; ++c) s += __expf(t[c] - m);
-      lse = m + __logf(s);
+      for (int c = 0; c < n; ++c) s += expf(t[c] - m);
+      lse = m + logf(s);
       if (a.labels) {
-        label = static_cast<int>(a.labels[row]);
-        if (label >= 0 && label < n) loss += lse - t[label];
+        const int64_t l64 = a.labels[row];
+        label = (l64 >= 0 && l64 < n) ? static_cast<int>(l64) : -1;     // outside [0, n): ignored row
+        if (label >= 0) { loss += lse - t[label]; valid += 1.f; }
       }
       // in place: t[c] <- log_softmax
       for (int c = 0; c < n; ++c) t[c] -= lse;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
 #pragma unroll 4
           for (int c = 0; c < 64; c += 2) {
             float v0 = c < n ? t[c] : 0.f, v1 = c + 1 < n ? t[c + 1] : 0.f;
-            if (a.mode == PCADV_HEAD_CE) { v0 = c < n ? __expf(v0) : 0.f; v1 = c + 1 < n ? __expf(v1) : 0.f; }
+            if (a.mode == PCADV_HEAD_CE) { v0 = c < n ? expf(v0) : 0.f; v1 = c + 1 < n ? expf(v1) : 0.f; }
             srow[c >> 1] = a.probs_dtype == PCADV_F16 ? pack_f16x2_sat(v0, v1) : pack_bf16x2(v0, v1);
           }
         }
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
       } else if (lane < nrows) {
         for (int c = 0; c < a.probs_cols; ++c) {
           float v = c < n ? t[c] : 0.f;
-          if (a.mode == PCADV_HEAD_CE && c < n) v = __expf(v);
+          if (a.mode == PCADV_HEAD_CE && c < n) v = expf(v);
           st_from_float(a.probs, row * a.ld_probs + c, a.probs_dtype, v);
         }
       }
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
           uint32_t* srow = stage + lane * kPitchW;
 #pragma unroll 4
           for (int c = 0; c < 64; c += 2) {
-            const float v0 = c < n ? a.dz_gain * (__expf(t[c]) - (c == label ? 1.f : 0.f)) : 0.f;
-            const float v1 = c + 1 < n ? a.dz_gain * (__expf(t[c + 1]) - (c + 1 == label ? 1.f : 0.f)) : 0.f;
+            const float v0 = (c < n && label >= 0) ? a.dz_gain * (expf(t[c]) - (c == label ? 1.f : 0.f)) : 0.f;
+            const float v1 = (c + 1 < n && label >= 0) ? a.dz_gain * (expf(t[c + 1]) - (c + 1 == label ? 1.f : 0.f)) : 0.f;
             srow[c >> 1] = a.dz_dtype == PCADV_F16 ? pack_f16x2_sat(v0, v1) : pack_bf16x2(v0, v1);
           }
         }
@@ -114,21 +115,25 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
         __syncwarp();
       } else if (lane < nrows) {
         for (int c = 0; c < a.dz_cols; ++c) {
-          const float v = c < n ? a.dz_gain * (__expf(t[c]) - (c == label ? 1.f : 0.f)) : 0.f;
+          const float v = (c < n && label >= 0) ? a.dz_gain * (expf(t[c]) - (c == label ? 1.f : 0.f)) : 0.f;
           st_from_float(a.dz, row * a.ld_dz + c, a.dz_dtype, v);
         }
       }
     }
   }
-  if (a.loss_sum) {
+  if (a.loss_sum || a.valid_count) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if (lane == 0) red[warp] = loss;
+    for (int o = 16; o >= 1; o >>= 1) {
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    }
+    if (lane == 0) { red[warp] = loss; red[8 + warp] = valid; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[w];
-      atomicAdd(a.loss_sum, s);
+      float s = 0.f, v = 0.f;
+      for (int w = 0; w < 8; ++w) { s += red[w]; v += red[8 + w]; }
+      if (a.loss_sum) atomicAdd(a.loss_sum, s);
+      if (a.valid_count) atomicAdd(a.valid_count, v);
     }
   }
 }
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const pcadv_head_args
 // warp shuffles, every load and store is one fully coalesced row segment.
 template <bool kBf16>
 __global__ void __launch_bounds__(256) softmax_head_rows_kernel(const pcadv_head_args a) {
-  __shared__ float red[8];
+  __shared__ float red[16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
   const bool col_ok = 2 * lane < n;                       // n is even: both columns of the pair exist
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(256) softmax_head_rows_kernel(const pcadv_head
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
   uint32_t* probs = reinterpret_cast<uint32_t*>(a.probs);
   uint32_t* dz = reinterpret_cast<uint32_t*>(a.dz);
-  float loss = 0.f;
+  float loss = 0.f, valid = 0.f;
   for (int64_t r0 = gwarp * 4; r0 < a.rows; r0 += nwarps * 4) {
     float2 t[4];
     int label[4];
@@ -157,7 +162,10 @@ __global__ void __launch_bounds__(256) softmax_head_rows_kernel(const pcadv_head
       label[u] = -1;
       if (r < a.rows) {
         if (col_ok) t[u] = __ldg(reinterpret_cast<const float2*>(a.logits + r * n) + lane);
-        if (a.labels) label[u] = static_cast<int>(__ldg(a.labels + r));
+        if (a.labels) {
+          const int64_t l64 = __ldg(a.labels + r);
+          label[u] = (l64 >= 0 && l64 < n) ? static_cast<int>(l64) : -1;   // outside [0, n): ignored row
+        }
       }
     }
     float m[4], s[4];
@@ -182,26 +190,32 @@ __global__ void __launch_bounds__(256) softmax_head_rows_kernel(const pcadv_head
       const float p0 = col_ok ? __expf(l0) : 0.f, p1 = col_ok ? __expf(l1) : 0.f;
       if (label[u] == 2 * lane) loss -= l0;
       else if (label[u] == 2 * lane + 1) loss -= l1;
+      if (lane == 0 && label[u] >= 0) valid += 1.f;
+      const bool live = label[u] >= 0;
       if (probs) {
         const float o0 = a.mode == PCADV_HEAD_LSM ? l0 : p0, o1 = a.mode == PCADV_HEAD_LSM ? l1 : p1;
         probs[r * 32 + lane] = kBf16 ? pack_bf16x2(o0, o1) : pack_f16x2_sat(o0, o1);
       }
       if (dz) {
-        const float d0 = col_ok ? a.dz_gain * (p0 - (label[u] == 2 * lane ? 1.f : 0.f)) : 0.f;
-        const float d1 = col_ok ? a.dz_gain * (p1 - (label[u] == 2 * lane + 1 ? 1.f : 0.f)) : 0.f;
+        const float d0 = (col_ok && live) ? a.dz_gain * (p0 - (label[u] == 2 * lane ? 1.f : 0.f)) : 0.f;
+        const float d1 = (col_ok && live) ? a.dz_gain * (p1 - (label[u] == 2 * lane + 1 ? 1.f : 0.f)) : 0.f;
         dz[r * 32 + lane] = kBf16 ? pack_bf16x2(d0, d1) : pack_f16x2_sat(d0, d1);
       }
     }
   }
-  if (a.loss_sum) {
+  if (a.loss_sum || a.valid_count) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if (lane == 0) red[warp] = loss;
+    for (int o = 16; o >= 1; o >>= 1) {
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    }
+    if (lane == 0) { red[warp] = loss; red[8 + warp] = valid; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      float sum = 0.f;
-      for (int w = 0; w < 8; ++w) sum += red[w];
-      atomicAdd(a.loss_sum, sum);
+      float sum = 0.f, v = 0.f;
+      for (int w = 0; w < 8; ++w) { sum += red[w]; v += red[8 + w]; }
+      if (a.loss_sum) atomicAdd(a.loss_sum, sum);
+      if (a.valid_count) atomicAdd(a.valid_count, v);
     }
   }
 }

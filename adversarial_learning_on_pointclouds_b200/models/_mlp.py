@@ -14,6 +14,17 @@ from ._chain import (Layer, ZeroPool, chain_forward, chain_backward, compute_wei
                      layer_wgrad, dgrad_weight)
 
 
+# Tests set this to a list: every PointMLPFunction.forward appends the activations it saved (the
+# branch decisions of the pass) -- tests/parity.py builds the oracle's ``branch`` dict from it.
+DEBUG_TAPE = None
+
+
+def _tape(spec, x_in, ys, red_val, red_idx, out, hit):
+    if DEBUG_TAPE is not None:
+        DEBUG_TAPE.append(dict(acts=list(spec.acts), reduce=spec.reduce, group=spec.group, x_in=x_in,
+                               ys=list(ys), red_val=red_val, red_idx=red_idx, out=out, cache_hit=hit))
+
+
 class MLPSpec:
     """Static description of a PointMLPFunction call.
 
@@ -53,13 +64,14 @@ class PointMLPFunction(torch.autograd.Function):
         # the detached tensor in the D phase (utils/trainer.py:916, :951-953).
         cache = _chain._WCACHE if gb is None and spec.tap is None else None
         fkey = None
+        x_key = x
         if cache is not None:
             ident = lambda t: None if t is None else (t.data_ptr(), tuple(t.shape), t.stride(), t._version, t.dtype)
             fkey = ("fwd", prec.name, tuple(spec.acts), spec.reduce, spec.group, ident(x),
                     tuple(ident(p_) for p_ in params))
             hit = cache.get(fkey)
             if hit is not None:
-                x_in, ys, ybits, red_val, red_idx, ctx.bcn, ctx.packed_in, out = hit
+                x_in, ys, ybits, red_val, red_idx, ctx.bcn, ctx.packed_in, out = hit[:8]
                 ctx.prec, ctx.spec = prec, spec
                 ctx.n_ys = len(ys)
                 ctx.has_red = red_val is not None
@@ -67,6 +79,7 @@ class PointMLPFunction(torch.autograd.Function):
                 ctx.bit_slots = [i for i, t in enumerate(ybits) if t is not None]
                 ctx.save_for_backward(*([x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) +
                                         list(params) + [ybits[i] for i in ctx.bit_slots]))
+                _tape(spec, x_in, ys, red_val, red_idx, out, True)
                 return out.detach()
         ctx.bcn = None
         ctx.packed_in = False
@@ -138,8 +151,11 @@ class PointMLPFunction(torch.autograd.Function):
         saved = [x_in] + ys + ([red_val, red_idx] if ctx.has_red else []) + list(params) + \
             [ybits[i] for i in ctx.bit_slots]
         ctx.save_for_backward(*saved)
+        _tape(spec, x_in, ys, red_val, red_idx, out, False)
         if fkey is not None:
-            cache[fkey] = (x_in, ys, ybits, red_val, red_idx, ctx.bcn, ctx.packed_in, out)
+            # the entry holds ``x`` itself (not only the converted copy): while it lives, the address
+            # the key was built from cannot be handed to another same-shaped temporary
+            cache[fkey] = (x_in, ys, ybits, red_val, red_idx, ctx.bcn, ctx.packed_in, out, x_key)
             return out.detach()
         if tap is not None:
             return out, tap
@@ -167,6 +183,10 @@ class PointMLPFunction(torch.autograd.Function):
         need_w = [need[2 * i] for i in range(nl)]
         need_b = [need[2 * i + 1] for i in range(nl)]
         need_x = ctx.needs_input_grad[2]
+        if ctx.packed_in and spec.box is None:
+            # a packed 16-bit map that reaches the discriminator as a fresh leaf (the history pool's
+            # clone, utils/image_pool.py:53-55): nobody consumes its gradient, so none is formed
+            need_x = False
         dev = x_in.device
         grads = [(None, None)] * nl
 
@@ -283,9 +303,9 @@ class PointMLPFunction(torch.autograd.Function):
             flat.append(dw.reshape(params[2 * i].shape) if dw is not None else None)
             flat.append(db)
         if ctx.packed_in and need_x:
-            if dx is None or dx.dtype != x_in.dtype or spec.box is None:
-                raise RuntimeError("a packed 16-bit input that requires grad needs a GradBox and a "
-                                   "layer chain in front of the reduction")
+            if dx is None or dx.dtype != x_in.dtype:
+                raise RuntimeError("a packed 16-bit input that requires grad needs a layer chain in "
+                                   "front of the reduction")
             spec.box.scale2 = scale2
         if dx is not None and ctx.bcn is not None:
             B_, C_, N_ = ctx.bcn                                # back to B x C x N (a view)

@@ -89,11 +89,15 @@ class SegFunction(torch.autograd.Function):
         if head == "logits":
             out, extra, keep = logits, None, None
         elif head == "ce":
-            loss_sum = torch.zeros(1, dtype=torch.float32, device=pts.device)
+            # [CE sum, number of rows with a label in [0, k)]: rows labelled outside that range are
+            # nn.CrossEntropyLoss's ignored rows (ignore_index = -100) and the mean is over the rest
+            acc = torch.zeros(2, dtype=torch.float32, device=pts.device)
             probs, u = ops.softmax_head(hs[3], HEAD_CE, labels=labels.reshape(-1).contiguous(),
                                         out_dtype=prec.act_dtype, cols=cols, want_dz=True,
-                                        dz_gain=HEAD_GAIN if prec.scaled else 1.0, loss_sum=loss_sum)
-            out = loss_sum[0] / float(P)
+                                        dz_gain=HEAD_GAIN if prec.scaled else 1.0, loss_sum=acc[0:1],
+                                        valid_count=acc[1:2])
+            ctx.ce_count = acc[1].clamp_min(1.0)
+            out = acc[0] / ctx.ce_count
             extra = probs.view(B, N, cols) if prec.scaled else probs.view(B, N, k_out).transpose(1, 2)
             keep = u
         elif head == "lsm":
@@ -101,8 +105,44 @@ class SegFunction(torch.autograd.Function):
             out = lp.view(B, N, cols) if prec.scaled else lp.view(B, N, k_out).transpose(1, 2)
             extra, keep = None, lp
             ctx.box = GradBox()
+        elif head == "ce+lsm":
+            # one pass over the labelled clouds (the first labels.shape[0] of the batch: CE + softmax,
+            # utils/trainer.py:898-901) and the unlabelled ones (log_softmax, :913-914) of an iteration
+            Bg = labels.shape[0]
+            Pg = Bg * N
+            acc = torch.zeros(2, dtype=torch.float32, device=pts.device)
+            dt = prec.act_dtype
+            # joint = [softmax(labelled) ; log_softmax(unlabelled)], what the discriminator reads;
+            # dzbuf = [gain * (softmax - onehot) ; filled by the backward], the dz of fc4
+            joint = torch.empty((P, cols), dtype=dt, device=pts.device)
+            dzbuf = torch.empty((P, cols), dtype=dt, device=pts.device)
+            if Pg > 0:
+                ops.softmax_head(hs[3][:Pg], HEAD_CE, labels=labels.reshape(-1).contiguous(), out_dtype=dt,
+                                 cols=cols, dz_gain=HEAD_GAIN if prec.scaled else 1.0, loss_sum=acc[0:1],
+                                 valid_count=acc[1:2], probs_out=joint[:Pg], dz_out=dzbuf[:Pg])
+            if P > Pg:
+                ops.softmax_head(hs[3][Pg:], HEAD_LSM, out_dtype=dt, cols=cols, probs_out=joint[Pg:])
+            ctx.ce_count = acc[1].clamp_min(1.0)
+            ctx.split = Bg
+            out = acc[0] / ctx.ce_count
+            if prec.scaled:
+                extra = joint[:Pg].view(Bg, N, cols)
+                lp_out = joint[Pg:].view(B - Bg, N, cols)
+            else:
+                extra = joint[:Pg].view(Bg, N, k_out).transpose(1, 2)
+                lp_out = joint[Pg:].view(B - Bg, N, k_out).transpose(1, 2)
+            ctx.box = GradBox()
+            ctx.has_keep = True
+            bit_list = xbits + hbits[:3]
+            ctx.bit_slots = [i for i, t in enumerate(bit_list) if t is not None]
+            ctx.save_for_backward(pts2, cls2, g, idx, *xs, *hs[:3], *params, joint, dzbuf,
+                                  *[bit_list[i] for i in ctx.bit_slots])
+            if debug is not None:
+                debug.update(x=xs, h=hs[:3], g=g, idx=idx, cbias=cbias, logits=logits)
+            ctx.mark_non_differentiable(extra)
+            return out, extra, lp_out, g
         else:
-            raise ValueError("head must be 'logits', 'ce' or 'lsm'")
+            raise ValueError("head must be 'logits', 'ce', 'lsm' or 'ce+lsm'")
         ctx.has_keep = keep is not None
         # 1-bit activation masks [x > 0] of x1..x5 / h1..h3 where the layer could emit them
         bit_list = xbits + hbits[:3]
@@ -125,12 +165,15 @@ class SegFunction(torch.autograd.Function):
             if d_out is None:
                 d_out = torch.zeros((), dtype=torch.float32, device=dev)
             d_out = d_out.float().reshape(())
+            cnt = ctx.ce_count                                     # rows that are not ignored
             if prec.scaled:
-                # dz_true = u * d_out / (GAIN * P): the kept u is the scaled dz with S = GAIN * P / d_out
-                inv = d_out / (HEAD_GAIN * P)
+                # dz_true = u * d_out / (GAIN * cnt): the kept u is the scaled dz with S = GAIN * cnt / d_out
+                inv = d_out / (HEAD_GAIN * cnt)
                 safe = torch.where(inv == 0, torch.ones_like(inv), inv)
                 return keep, torch.stack([1.0 / safe, inv])
-            return keep * (d_out / P), None
+            return keep * (d_out / cnt), None
+        if ctx.head == "ce+lsm":
+            return SegFunction._dual_head_dz(ctx, prec, keep, d_out, B, N, k_out, dev)
         # "lsm": d_out is the gradient of the packed log-softmax map
         if prec.scaled:
             scale2 = ctx.box.scale2
@@ -155,6 +198,50 @@ class SegFunction(torch.autograd.Function):
         return ops.logsoftmax_bwd(keep, d2, k_out), None
 
     @staticmethod
+    def _dual_head_dz(ctx, prec, keep, d_out, B, N, k_out, dev):
+        """dz of fc4 for the "ce+lsm" head: rows of the labelled clouds carry the CE gradient the
+        forward stored, rows of the unlabelled ones the log_softmax backward of the discriminator's
+        gradient.  Both halves share ONE gradient scale, the CE half's S = GAIN * count / dloss (the
+        adversarial rows are rescaled from the scale the discriminator's backward left in the box)."""
+        joint, dzbuf = keep
+        d_loss, d_lp = d_out
+        Pg = ctx.split * N
+        P = B * N
+        if d_loss is None:
+            d_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        d_loss = d_loss.float().reshape(())
+        cnt = ctx.ce_count
+        lp = joint[Pg:]
+        if prec.scaled:
+            inv = d_loss / (HEAD_GAIN * cnt)
+            safe = torch.where(inv == 0, torch.ones_like(inv), inv)
+            scale2 = torch.stack([1.0 / safe, inv])
+            box2 = ctx.box.scale2
+            ctx.box.scale2 = None
+            if P > Pg:
+                if d_lp is None:
+                    dzbuf[Pg:].zero_()
+                else:
+                    d2 = d_lp.reshape(P - Pg, joint.shape[1])
+                    if d2.stride(1) != 1:
+                        d2 = d2.contiguous()
+                    # incoming rows carry the discriminator's scale S_D: bring them to S
+                    ratio = scale2[0:1] * box2[1:2] if box2 is not None else scale2[0:1].clone()
+                    ops.logsoftmax_bwd(lp, d2, k_out, scale=ratio, cols=joint.shape[1], out=dzbuf[Pg:])
+            return dzbuf, scale2
+        dz_g = dzbuf[:Pg] * (d_loss / cnt)
+        if P == Pg:
+            return dz_g, None
+        if d_lp is None:
+            dz_n = torch.zeros((P - Pg, k_out), dtype=torch.float32, device=dev)
+        else:
+            d2 = d_lp.transpose(1, 2).reshape(P - Pg, k_out)
+            if d2.stride(1) != 1 or d2.dtype != torch.float32:
+                d2 = d2.contiguous().float()
+            dz_n = ops.logsoftmax_bwd(lp, d2, k_out)
+        return torch.cat([dz_g, dz_n], 0), None
+
+    @staticmethod
     def backward(ctx, dlogits, *rest):
         prec = ctx.prec
         B, N = ctx.shape
@@ -169,8 +256,13 @@ class SegFunction(torch.autograd.Function):
             bit_list[slot] = t
         xbits, hbits = bit_list[:5], bit_list[5:]
         sv = sv[:len(sv) - nb]
-        keep = sv[-1] if ctx.has_keep else None
-        params = sv[12:-1] if ctx.has_keep else sv[12:]
+        if ctx.head == "ce+lsm":
+            keep = (sv[-2], sv[-1])
+            params = sv[12:-2]
+            dlogits = (dlogits, rest[1])              # (d loss, d log_softmax map); rest[0]: softmax, no grad
+        else:
+            keep = sv[-1] if ctx.has_keep else None
+            params = sv[12:-1] if ctx.has_keep else sv[12:]
         p = dict(zip(PARAM_NAMES, params))
         need = dict(zip(PARAM_NAMES, ctx.needs_input_grad[6:]))
         W = {n: p[n + ".weight"].reshape(p[n + ".weight"].shape[0], -1) for n in _TRUNK + _HEAD}

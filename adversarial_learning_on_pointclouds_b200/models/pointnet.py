@@ -180,6 +180,22 @@ class PointNetSeg(nn.Module):
                                            *_params(self, _SEG_PARAMS))
         return loss, probs, g.unsqueeze(2)
 
+    def forward_ce_logsoftmax(self, x, cls, seg, x_nogt, cls_nogt):
+        """Both generator passes of one adversarial iteration (utils/trainer.py:898-901 and :913-914)
+        as ONE pass over the labelled and the unlabelled clouds: -> (CrossEntropyLoss(pred, seg) of
+        the labelled clouds, softmax(pred) of the labelled clouds [no grad], log_softmax(pred) of the
+        unlabelled clouds [differentiable], global feature of all clouds (B + B') x 2048 x 1).  Clouds
+        are independent through the whole network, so this equals forward_ce + forward_logsoftmax."""
+        if x.shape[1] != x_nogt.shape[1]:
+            raise ValueError("labelled and unlabelled clouds need the same number of points")
+        loss, probs, lp, g = SegFunction.apply(_prec(self), self._debug, "ce+lsm", seg,
+                                               torch.cat([x, x_nogt], 0), torch.cat([cls, cls_nogt], 0),
+                                               *_params(self, _SEG_PARAMS))
+        node = lp.grad_fn
+        if node is not None and getattr(node, "box", None) is not None:
+            lp._pcadv_box = node.box
+        return loss, probs, lp, g.unsqueeze(2)
+
     def forward_logsoftmax(self, x, cls):
         """-> (log_softmax(pred, dim=1) as a differentiable discriminator input, global)."""
         lp, g = SegFunction.apply(_prec(self), self._debug, "lsm", None, x, cls,

@@ -487,10 +487,13 @@ def convert_cm(x_bcn, out_dtype, cols_pad=None, scale=None):
 
 
 def softmax_head(logits, mode, *, labels=None, out_dtype=torch.float32, cols=None, want_probs=True,
-                 want_dz=False, dz_gain=1.0, loss_sum=None):
+                 want_dz=False, dz_gain=1.0, loss_sum=None, valid_count=None, probs_out=None, dz_out=None):
     """See ``pcadv_softmax_head``.  logits: fp32 [rows, n].  Returns (probs | None, dz | None): point-
     major [rows, cols] matrices of ``out_dtype`` (softmax, or log_softmax in HEAD_LSM mode, and
-    dz_gain * (softmax - onehot)); ``loss_sum`` (fp32 scalar tensor) accumulates the CE sum."""
+    dz_gain * (softmax - onehot)); ``loss_sum`` (fp32 scalar tensor) accumulates the CE sum and
+    ``valid_count`` the number of rows whose label lies in [0, n) (other rows are ignored rows:
+    no loss term, zero dz).  ``probs_out`` / ``dz_out``: caller-owned [rows, cols] destinations (row
+    slices of a larger matrix) instead of fresh tensors."""
     a = _lib.HeadArgs()
     p, ld, dt = _mat(logits)
     if dt != F32:
@@ -503,14 +506,25 @@ def softmax_head(logits, mode, *, labels=None, out_dtype=torch.float32, cols=Non
             raise ValueError("labels must be a contiguous int64 tensor with one entry per row")
         a.labels = _ptr(labels)
     probs = dz = None
-    if want_probs:
-        probs = torch.empty((rows, cols), dtype=out_dtype, device=logits.device)
-        a.probs, a.ld_probs, a.probs_dtype, a.probs_cols = _ptr(probs), cols, _DT[out_dtype], cols
-    if want_dz:
-        dz = torch.empty((rows, cols), dtype=out_dtype, device=logits.device)
-        a.dz, a.ld_dz, a.dz_dtype, a.dz_cols = _ptr(dz), cols, _DT[out_dtype], cols
+
+    def dest(given):
+        if given is None:
+            return torch.empty((rows, cols), dtype=out_dtype, device=logits.device)
+        if tuple(given.shape) != (rows, cols) or given.dtype != out_dtype or (cols > 1 and given.stride(1) != 1):
+            raise ValueError("softmax_head destination must be [%d, %d] %s with unit column stride"
+                             % (rows, cols, out_dtype))
+        return given
+
+    if want_probs or probs_out is not None:
+        probs = dest(probs_out)
+        a.probs, a.ld_probs, a.probs_dtype, a.probs_cols = _ptr(probs), probs.stride(0) if rows > 1 else cols, \
+            _DT[out_dtype], cols
+    if want_dz or dz_out is not None:
+        dz = dest(dz_out)
+        a.dz, a.ld_dz, a.dz_dtype, a.dz_cols = _ptr(dz), dz.stride(0) if rows > 1 else cols, _DT[out_dtype], cols
     a.dz_gain = float(dz_gain)
     a.loss_sum = _f32(loss_sum) if loss_sum is not None else None
+    a.valid_count = _f32(valid_count) if valid_count is not None else None
     if rows == 0:
         return probs, dz
     _call("softmax_head:%s" % ("ce" if mode == _lib.HEAD_CE else "lsm"), _lib.lib().pcadv_softmax_head,
@@ -518,18 +532,24 @@ def softmax_head(logits, mode, *, labels=None, out_dtype=torch.float32, cols=Non
     return probs, dz
 
 
-def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None):
+def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None, out=None):
     """dz = scale * (dy - exp(lp) * rowsum(dy)) over the first ``n`` columns (see
     ``pcadv_logsoftmax_bwd``); returns [rows, cols] of ``out_dtype`` (zero beyond n)."""
     lpp, ld_lp, lpd = _mat(lp)
     dyp, ld_dy, dyd = _mat(dy)
     rows = lp.shape[0]
     cols = int(cols or n)
-    dz = torch.empty((rows, cols), dtype=out_dtype, device=lp.device)
+    if out is not None:
+        if tuple(out.shape) != (rows, cols) or (cols > 1 and out.stride(1) != 1):
+            raise ValueError("logsoftmax_bwd: out must be [%d, %d] with unit column stride" % (rows, cols))
+        dz, out_dtype = out, out.dtype
+    else:
+        dz = torch.empty((rows, cols), dtype=out_dtype, device=lp.device)
     if rows == 0:
         return dz
     _call("logsoftmax_bwd", _lib.lib().pcadv_logsoftmax_bwd, lpp, lpd, ld_lp, dyp, dyd, ld_dy, rows, int(n),
-          _f32(scale) if scale is not None else None, _ptr(dz), _DT[out_dtype], cols, cols, _stream())
+          _f32(scale) if scale is not None else None, _ptr(dz), _DT[out_dtype],
+          dz.stride(0) if rows > 1 else cols, cols, _stream())
     return dz
 
 

@@ -75,6 +75,7 @@ def _adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimiz
     D_out = model_D(pred_nogt_softmax)
     loss_adv = gan_loss(D_out, label(D_out, gt_label, False))
     (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()
+    _start_reduce(optimizer)
 
     # ---- train D (:931-963)
     for param in model_D.parameters():
@@ -91,18 +92,35 @@ def _adversarial_seg_step(model, model_D, gan_loss, seg_loss, optimizer, optimiz
     return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
 
 
+def _start_reduce(optimizer):
+    """Data-parallel runs (parallel.DistributedOptimizer): launch this optimizer's gradient
+    all-reduce now, asynchronously; ``optimizer.step()`` waits for it.  A plain optimizer has no
+    such hook and nothing happens."""
+    start = getattr(optimizer, "reduce_gradients_async", None)
+    if start is not None:
+        start()
+
+
 def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
                                 batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
-                                device_labels=False, label_fn=None):
+                                device_labels=False, label_fn=None, one_pass=None):
     """The same iteration (utils/trainer.py:873-966) through the generator's fused loss heads
     (SURVEY.md 8f rank 1): ``CrossEntropyLoss`` + ``softmax`` of the labelled pass and
     ``log_softmax`` of the unlabelled pass are one kernel each over the logits, and the
     discriminator reads their packed 16-bit output directly.  ``seg_loss`` must be
     ``nn.CrossEntropyLoss()`` with default arguments (mean over all points); it is accepted only
-    to keep the signature of ``adversarial_seg_step``.  Same losses, same gradients."""
+    to keep the signature of ``adversarial_seg_step``.  Same losses, same gradients.
+
+    ``one_pass`` (default: when the loss weights allow it): the two generator passes of the
+    iteration run as ONE pass over the labelled + unlabelled clouds (``forward_ce_logsoftmax``):
+    clouds are independent through the network, so the sums are the same, with half the launches and
+    no gradient accumulation between two backward passes."""
     if not isinstance(seg_loss, torch.nn.CrossEntropyLoss) or seg_loss.weight is not None or \
             seg_loss.reduction != "mean" or seg_loss.label_smoothing != 0.0:
         raise ValueError("the fused step implements nn.CrossEntropyLoss() with default arguments")
+    if 0 <= seg_loss.ignore_index < model.output_dim:
+        # the fused head ignores exactly the labels outside [0, k) (the default ignore_index = -100)
+        raise ValueError("the fused step cannot ignore a label inside [0, %d)" % model.output_dim)
     gt_label, nogt_label = 1, 0
     pool_gt = history_pool_gt or ImagePool(0)
     pool_nogt = history_pool_nogt or ImagePool(0)
@@ -122,12 +140,22 @@ def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, o
     for param in model_D.parameters():
         param.requires_grad = False
     pts, cls, seg = batch_gt
-    l_seg, pred_gt_softmax, _ = model.forward_ce(pts, cls, seg)          # :898-901
     pts_nogt, cls_nogt = batch_nogt
-    pred_nogt_softmax, _ = model.forward_logsoftmax(pts_nogt, cls_nogt)   # :913-914
+    if one_pass is None:
+        # One generator pass over the labelled + unlabelled clouds shares one gradient scale, the CE
+        # rows'; that needs a CE term and an adversarial term that is not orders of magnitude larger.
+        one_pass = (args.lambda_seg > 0 and args.lambda_adv <= 4.0 * args.lambda_seg
+                    and pts.shape[1] == pts_nogt.shape[1] and hasattr(model, "forward_ce_logsoftmax"))
+    if one_pass:
+        l_seg, pred_gt_softmax, pred_nogt_softmax, _ = model.forward_ce_logsoftmax(
+            pts, cls, seg, pts_nogt, cls_nogt)                            # :898-901 and :913-914
+    else:
+        l_seg, pred_gt_softmax, _ = model.forward_ce(pts, cls, seg)          # :898-901
+        pred_nogt_softmax, _ = model.forward_logsoftmax(pts_nogt, cls_nogt)   # :913-914
     D_out = model_D(pred_nogt_softmax)
     loss_adv = gan_loss(D_out, label(D_out, gt_label, False))
     (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()
+    _start_reduce(optimizer)       # G's gradients are final: their all-reduce runs under the D phase
 
     for param in model_D.parameters():
         param.requires_grad = True
@@ -213,6 +241,41 @@ def adversarial_cls_step(model, model_D, gan_loss, cls_loss, optimizer, optimize
     return l_cls.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
 
 
+def _optimizers_of(opt):
+    return getattr(opt, "optimizer", opt)
+
+
+def _snapshot_training_state(models, optimizers):
+    """Clones of every parameter and optimizer-state tensor (and the device generator state)."""
+    params = [[p.detach().clone() for p in m.parameters()] for m in models]
+    states = []
+    for opt in optimizers:
+        st = _optimizers_of(opt).state
+        states.append({id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+                       for p, d in st.items()})
+    return params, states, torch.cuda.get_rng_state()
+
+
+def _restore_training_state(snap, models, optimizers):
+    """In-place restore (the tensors keep their addresses, so a later graph capture sees them).
+    Optimizer-state tensors that did not exist at snapshot time are zeroed, which is the state a
+    fresh Adam / momentum-free SGD starts from."""
+    params, states, rng = snap
+    with torch.no_grad():
+        for m, saved in zip(models, params):
+            for p, s in zip(m.parameters(), saved):
+                p.copy_(s)
+            for p in m.parameters():
+                p.grad = None
+        for opt, saved in zip(optimizers, states):
+            for p, d in _optimizers_of(opt).state.items():
+                old = saved.get(id(p), {})
+                for k, v in d.items():
+                    if torch.is_tensor(v):
+                        v.copy_(old[k]) if k in old else v.zero_()
+    torch.cuda.set_rng_state(rng)
+
+
 class GraphedAdversarialSegStep:
     """``adversarial_seg_step`` captured once into a CUDA graph and replayed.
 
@@ -223,10 +286,23 @@ class GraphedAdversarialSegStep:
     CPU from torch's default generator): they are drawn into pinned host buffers and copied to
     static device buffers before every replay.  Optimizers must be built with
     ``capturable=True``.
+
+    The constructor runs ``warmup`` iterations on the first batch before capturing (allocator
+    warm-up, lazy optimizer state).  With ``restore_state`` (default) the parameters, the optimizer
+    state and the device generator are restored in place afterwards, so constructing the object
+    does not advance training; the CPU generator is only consumed by the label draws of the real
+    iterations, in the reference's order.
     """
 
     def __init__(self, model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, args, batch_gt,
-                 batch_nogt, warmup=3, device_labels=False, fused=False):
+                 batch_nogt, warmup=3, device_labels=False, fused=False, restore_state=True,
+                 history_pool_gt=None, history_pool_nogt=None, one_pass=None):
+        for pool in (history_pool_gt, history_pool_nogt):
+            if pool is not None and getattr(pool, "pool_size", 0) > 0:
+                # the pool's swap decisions are host-side ``random`` draws per sample
+                # (utils/image_pool.py:38-52): they cannot be replayed from a captured graph
+                raise ValueError("GraphedAdversarialSegStep supports pool_size == 0 only; use "
+                                 "adversarial_seg_step(_fused) for history pools")
         self.static_gt = tuple(t.clone() for t in batch_gt)
         self.static_nogt = tuple(t.clone() for t in batch_nogt)
         self.device_labels = device_labels
@@ -250,19 +326,28 @@ class GraphedAdversarialSegStep:
 
         step_fn = adversarial_seg_step_fused if fused else adversarial_seg_step
 
+        extra = {"one_pass": one_pass} if fused else {}
+
         def run():
             return step_fn(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D,
-                           self.static_gt, self.static_nogt, args, label_fn=label_fn)
+                           self.static_gt, self.static_nogt, args, label_fn=label_fn, **extra)
 
         self._draw_labels(0)
         self._upload_labels()
+        # The warm-up iterations (allocator / lazy optimizer state before capture) are real optimizer
+        # steps; they must not count as training: parameters, optimizer state and the device
+        # generator are put back afterwards, in place, so the first replay is iteration 1 of the
+        # reference loop (utils/trainer.py:873) from the caller's state.
+        snap = _snapshot_training_state((model, model_D), (optimizer, optimizer_D)) if restore_state else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):
                 run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if snap is not None:
+            _restore_training_state(snap, (model, model_D), (optimizer, optimizer_D))
         from . import _lib
         before = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()

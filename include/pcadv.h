@@ -275,7 +275,8 @@ int pcadv_convert_cm(const float* src, int64_t batch_stride, int64_t chan_stride
  *     probs[r, c]  = softmax(logits[r, :])[c]                       F.softmax(pred, dim=1)
  *     dz[r, c]     = dz_gain * (probs[r, c] - [c == labels[r]])     d CrossEntropyLoss / d logits,
  *                                                                   up to the 1 / rows mean factor
- *     *loss_sum   += sum_r (logsumexp(logits[r, :]) - logits[r, labels[r]])
+ *     *loss_sum   += sum_r (logsumexp(logits[r, :]) - logits[r, labels[r]])   over rows with a label in [0, n)
+ *     *valid_count += the number of such rows (the mean's denominator)
  *   mode PCADV_HEAD_LSM (unlabelled batch, utils/trainer.py:914)
  *     probs[r, c]  = log_softmax(logits[r, :])[c]
  * probs / dz are point-major [rows, *_cols] matrices of *_dtype, zero-filled in the columns
@@ -300,6 +301,9 @@ typedef struct pcadv_head_args {
   int32_t dz_cols;
   float dz_gain;
   float* loss_sum;            /* device scalar, accumulated into, or NULL */
+  float* valid_count;         /* device scalar += #rows with labels[r] in [0, n), or NULL.  Rows whose label
+                                 is outside [0, n) are IGNORED rows (nn.CrossEntropyLoss's ignore_index,
+                                 -100 by default): no loss term, dz row = 0. */
 } pcadv_head_args;
 
 int pcadv_softmax_head(const pcadv_head_args* a, void* stream);

@@ -56,7 +56,35 @@ def _worker(rank, world, port, out_dir):
         want = sd[k] - 0.1 * ref[k].grad
         worst = max(worst, ((params[k].detach() - want).norm() / want.norm().clamp_min(1e-12)).item())
     assert worst < 1e-5, worst
-    assert unused.grad is not None and float(unused.grad.abs().sum()) == 0.0
+    assert opt.last_mode == "packed"                             # torch autograd: one storage per gradient
+    assert unused.grad is None                                   # as in a single process: Adam / SGD skip it
+    # ---- second iteration with zero_grad(set_to_none=False): gradients accumulate into the
+    # same tensors, which must not alias the exchange buffer
+    before = {k: v.detach().clone() for k, v in params.items()}
+    opt.zero_grad(set_to_none=False)
+    _loss(params, *my).backward()
+    opt.reduce_gradients_async()                                 # started early, as the step functions do
+    opt.reduce_gradients_async()                                 # idempotent
+    opt.step()
+    ref2 = steps.leaf_params(before)
+    _loss(ref2, pts, cls, seg).backward()
+    for k in params:
+        want = before[k] - 0.1 * ref2[k].grad
+        worst = max(worst, ((params[k].detach() - want).norm() / want.norm().clamp_min(1e-12)).item())
+    assert worst < 1e-5, worst
+    # ---- in-place exchange: gradients that are views of one zero-filled slab (what the libpcadv
+    # backward hands autograd) are reduced where they lie
+    ws = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+    opt2 = DistributedOptimizer(torch.optim.SGD(ws, lr=1.0))
+    slab = torch.zeros(40)
+    ws[0].grad = slab[0:15].view(5, 3)
+    ws[1].grad = slab[16:23]
+    slab[0:15] = float(rank + 1)
+    slab[16:23] = float(10 * (rank + 1))
+    opt2.step()
+    assert opt2.last_mode == "in_place"
+    assert ws[0].grad.untyped_storage().data_ptr() == slab.untyped_storage().data_ptr()
+    assert torch.allclose(ws[0].detach(), torch.full((5, 3), -1.5)) and torch.allclose(ws[1].detach(), torch.full((7,), -15.0))
     flat = torch.cat([p.detach().reshape(-1) for p in params.values()])
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
