@@ -296,7 +296,7 @@ class GraphedAdversarialSegStep:
 
     def __init__(self, model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, args, batch_gt,
                  batch_nogt, warmup=3, device_labels=False, fused=False, restore_state=True,
-                 history_pool_gt=None, history_pool_nogt=None, one_pass=None):
+                 history_pool_gt=None, history_pool_nogt=None, one_pass=None, label_draw=None):
         for pool in (history_pool_gt, history_pool_nogt):
             if pool is not None and getattr(pool, "pool_size", 0) > 0:
                 # the pool's swap decisions are host-side ``random`` draws per sample
@@ -306,6 +306,10 @@ class GraphedAdversarialSegStep:
         self.static_gt = tuple(t.clone() for t in batch_gt)
         self.static_nogt = tuple(t.clone() for t in batch_nogt)
         self.device_labels = device_labels
+        # label_draw(real, fake): fills the two pinned host label buffers of the next iteration;
+        # default = the reference's draws (utils/utils.py:22-31).  Data-parallel parity tests pass
+        # their shard of globally drawn labels here.
+        self.label_draw = label_draw
         B, N = batch_nogt[0].shape[0], batch_nogt[0].shape[1]
         Bg = batch_gt[0].shape[0]
         dev = batch_gt[0].device
@@ -391,6 +395,9 @@ class GraphedAdversarialSegStep:
             return
         if self._copied[slot] is not None:
             self._copied[slot].synchronize()          # its previous upload has left the buffer
+        if self.label_draw is not None:
+            self.label_draw(self.host_real[slot], self.host_fake[slot])
+            return
         self.host_real[slot].uniform_(0.7, 1.05)
         self.host_fake[slot].uniform_(0.0, 0.305)
 

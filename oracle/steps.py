@@ -34,7 +34,8 @@ def _set_requires_grad(params, flag):
 
 
 def adversarial_seg_step(g_params, d_params, batch_gt, batch_nogt, disc="pointwise",
-                         lambda_seg=1.0, lambda_adv=1e-3, labels=None, generator=None):
+                         lambda_seg=1.0, lambda_adv=1e-3, labels=None, generator=None,
+                         branch=None, record=None):
     """One iteration of ``run_training_seg`` (utils/trainer.py:873-966) with
     history pools of size 0 (pass-through, utils/image_pool.py:35-36).
 
@@ -45,35 +46,41 @@ def adversarial_seg_step(g_params, d_params, batch_gt, batch_nogt, disc="pointwi
 
     ``labels``: optional (real_label, fake_label) tensors replacing the two
     random ``make_D_label`` draws at :940-945 and :955-960.
+    ``branch`` / ``record``: optional dicts keyed by pass -- "g_gt", "g_nogt" (the two generator
+    passes), "d_adv", "d_gt", "d_nogt" (the three discriminator passes) -- holding the per-pass
+    ``branch`` / ``record`` dicts of the model oracles (branch-conditioned parity).
     Returns dict(l_seg, l_adv, l_D_gt, l_D_nogt) of Python floats.
     """
     pts, cls, seg = batch_gt
     pts_nogt, cls_nogt = batch_nogt
     n_pts = pts.shape[1]
+    br = (lambda k: branch.get(k)) if branch is not None else (lambda k: None)
+    rc = (lambda k: record.setdefault(k, {})) if record is not None else (lambda k: None)
 
-    def run_D(x):
+    def run_D(x, which):
         if disc == "pointwise":
-            return D.pointwise_disc_forward(d_params, x, n_pts)
-        return D.conv_disc_forward(d_params, x.transpose(1, 2))
+            return D.pointwise_disc_forward(d_params, x, n_pts, branch=br(which), record=rc(which))
+        return D.conv_disc_forward(d_params, x.transpose(1, 2), branch=br(which), record=rc(which))
 
     # ---- train G (:884-929): D frozen
     _set_requires_grad(d_params, False)
-    pred, _ = P.pointnet_seg_forward(g_params, pts, cls)                      # :898
+    pred, _ = P.pointnet_seg_forward(g_params, pts, cls, branch=br("g_gt"), record=rc("g_gt"))   # :898
     l_seg = F.cross_entropy(pred, seg)                                        # :899
     pred_gt_softmax = F.softmax(pred, dim=1)                                  # :901
-    pred_nogt, _ = P.pointnet_seg_forward(g_params, pts_nogt, cls_nogt)       # :913
+    pred_nogt, _ = P.pointnet_seg_forward(g_params, pts_nogt, cls_nogt, branch=br("g_nogt"),
+                                          record=rc("g_nogt"))                # :913
     pred_nogt_softmax = F.log_softmax(pred_nogt, dim=1)                       # :914
-    D_out = run_D(pred_nogt_softmax)                                          # :916
+    D_out = run_D(pred_nogt_softmax, "d_adv")                                 # :916
     l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False, device=D_out.device))
     (lambda_seg * l_seg + lambda_adv * l_adv).backward()                      # :927-929
 
     # ---- train D (:931-963)
     _set_requires_grad(d_params, True)
-    D_out = run_D(pred_gt_softmax.detach())                                   # :936-938
+    D_out = run_D(pred_gt_softmax.detach(), "d_gt")                           # :936-938
     lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator, D_out.device)
     l_D_gt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5             # :946-947
     l_D_gt.backward()
-    D_out = run_D(pred_nogt_softmax.detach())                                 # :951-953
+    D_out = run_D(pred_nogt_softmax.detach(), "d_nogt")                       # :951-953
     lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator, D_out.device)
     l_D_nogt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5           # :961-962
     l_D_nogt.backward()

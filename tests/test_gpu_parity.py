@@ -139,8 +139,10 @@ def _seg_on_gpu(wseed, bseed, mode):
 def test_seg_matches_oracle(mode, B, N):
     net = _seg_on_gpu(3, 11, mode)
     pts, _, seg, cls = inputs(B, N, 77)
-    rep = parity.seg_parity(net, pts.to(DEV), cls.to(DEV), seg.to(DEV), TOL[mode])
-    print(mode, B, N, rep["pred"], rep["grad_total"], rep["n_branch_diff"])
+    rep = parity.seg_parity(net, pts.to(DEV), cls.to(DEV), seg.to(DEV), TOL[mode], mode=mode)
+    print(mode, B, N, rep["pred"], rep["grad_total"], rep["n_branch_diff"],
+          "worst flipped margins: act %.2f u, argmax %.2f u" % (rep["worst_act_margin_u"],
+                                                               rep["worst_argmax_margin_u"]))
     if mode == "fp32":
         assert rep["n_branch_diff"] <= 2          # exact-rounding ties only
 
