@@ -306,10 +306,51 @@ __global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(
   }
 }
 
+
+// Column sums of what a 16-bit conversion drops: out[c] += sum_r (v - round16(v)), v = src[r, c] * scale.
+// A bias gradient is a plain sum over rows of dz; when dz is stored in 16 bits and its entries barely
+// vary from row to row (softmax - onehot of a freshly initialised head: every entry ~1/k), the
+// roundings are coherent and their sum grows like the row count instead of its square root.  The
+// caller adds (*inv_scale) * out to the bias gradient formed from the 16-bit dz, which makes it the
+// exact fp32 column sum the reference's autograd computes.
+__global__ void __launch_bounds__(256) round_residual_kernel(const float* __restrict__ src, int64_t ld,
+                                                             int64_t rows, int cols, const float* scale,
+                                                             int dtype, float* out) {
+  __shared__ float red[4][64];
+  const int c = threadIdx.x & 63, sub = threadIdx.x >> 6;          // 64 columns x 4 row lanes
+  const float sc = scale ? *scale : 1.f;
+  float acc = 0.f;
+  if (c < cols) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 4 + sub; r < rows; r += static_cast<int64_t>(gridDim.x) * 4) {
+      const float v = __ldg(src + r * ld + c) * sc;
+      float q;
+      if (dtype == PCADV_F16) q = __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+      else q = __bfloat162float(__float2bfloat16_rn(v));
+      acc += v - q;
+    }
+  }
+  red[sub][c] = acc;
+  __syncthreads();
+  if (sub == 0 && c < cols) atomicAdd(out + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+}
+
 }  // namespace
 }  // namespace pcadv
 
 using namespace pcadv;
+
+extern "C" int pcadv_round_residual(const float* src, int64_t ld, int64_t rows, int32_t cols, const float* scale,
+                                    int32_t dtype, float* out, void* stream) {
+  PCADV_CHECK_ARG(src && out && rows >= 0 && cols > 0 && cols <= 64 && (dtype == PCADV_F16 || dtype == PCADV_BF16),
+                  "pcadv_round_residual: bad args (1 <= cols <= 64, 16-bit dtype)");
+  if (rows == 0) return 0;
+  int64_t grid = (rows + 3) / 4;
+  if (grid > 148 * 8) grid = 148 * 8;
+  round_residual_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld, rows, cols, scale, dtype, out);
+  PCADV_LAUNCHED();
+  return 0;
+}
 
 extern "C" int pcadv_softmax_head(const pcadv_head_args* a, void* stream) {
   PCADV_CHECK_ARG(a && a->logits && a->rows >= 0 && a->n > 0 && a->n <= kHeadMaxN,

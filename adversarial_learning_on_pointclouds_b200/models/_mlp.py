@@ -214,11 +214,17 @@ class PointMLPFunction(torch.autograd.Function):
         body = layers if spec.reduce is None else layers[:-1]
         dz_last = None
         dx = dz0 = None
+        db_residual = None
         if spec.reduce is None:
             if d_out is not None:
                 L = layers[-1]
                 dz_last = prepare_dz(prec, d_out, scale2, mask=ys[-1], mask_act=L.act,
                                      mask_slope=L.slope)
+                if prec.scaled and L.act == ACT_NONE and need_b[-1] and d_out.dim() == 2 and d_out.shape[1] <= 64:
+                    # the last bias gradient is a plain column sum of d_out: give back what the
+                    # 16-bit dz dropped, so that it is the exact fp32 sum (coherent roundings of
+                    # nearly constant columns would otherwise add up over the rows)
+                    db_residual = ops.round_residual(d_out, S, prec.act_dtype)
         elif d_out is not None:
             L = layers[-1]
             src = ys[-1] if ys else x_in
@@ -291,6 +297,8 @@ class PointMLPFunction(torch.autograd.Function):
                                          pool=pool)
             for i, gr in enumerate(g2):
                 grads[i] = gr
+        if db_residual is not None and grads[-1] is not None and grads[-1][1] is not None:
+            grads[-1][1].add_(db_residual[:grads[-1][1].shape[0]] * inv)
         dgb = None
         if ctx.has_gb and ctx.needs_input_grad[3] and dz0 is not None:
             rows, n0 = dz0.shape[0], layers[0].w.shape[0]

@@ -553,6 +553,20 @@ def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None,
     return dz
 
 
+def round_residual(src, scale, out_dtype):
+    """Column sums of what converting ``src * scale`` (fp32 [rows, cols <= 64]) to ``out_dtype`` drops:
+    see ``pcadv_round_residual``.  Returns fp32 [cols]."""
+    p, ld, dt = _mat(src)
+    if dt != F32:
+        raise ValueError("round_residual expects fp32")
+    rows, cols = src.shape
+    out = torch.zeros((cols,), dtype=torch.float32, device=src.device)
+    if rows > 0:
+        _call("round_residual", _lib.lib().pcadv_round_residual, p, ld, rows, cols,
+              _f32(scale) if scale is not None else None, _DT[out_dtype], _ptr(out), _stream())
+    return out
+
+
 def _f32c(t):
     if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
         raise ValueError("expected a contiguous fp32 CUDA tensor")

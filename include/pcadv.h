@@ -315,6 +315,13 @@ int pcadv_logsoftmax_bwd(const void* lp, int32_t lp_dtype, int64_t ld_lp, const 
                          int32_t dy_dtype, int64_t ld_dy, int64_t rows, int32_t n, const float* scale,
                          void* dz, int32_t dz_dtype, int64_t ld_dz, int32_t dz_cols, void* stream);
 
+/* out[c] += sum_r (v - round_dtype(v)), v = src[r, c] * (*scale): the column sums of what the 16-bit
+ * conversion of a gradient matrix drops (dtype = PCADV_F16 | PCADV_BF16, cols <= 64; the caller
+ * zero-fills out).  Added to a bias gradient formed from the 16-bit dz it restores the exact fp32
+ * column sum of the reference's autograd (the `.sum(0)` of a Linear / Conv1d bias gradient). */
+int pcadv_round_residual(const float* src, int64_t ld, int64_t rows, int32_t cols, const float* scale,
+                         int32_t dtype, float* out, void* stream);
+
 /*
  * T-Net transforms (fp32, k <= 128), one launch per op instead of one torch.bmm per cloud.
  *   pcadv_bmm:       y[g, r, :] = x[g, r, :] @ T[g]  (transpose_t = 0)  or  @ T[g]^T  (= 1, the backward dx)

@@ -137,6 +137,148 @@ def pointnet_cls_step(g_params, batch, feature_transform=False, lambda_cls=1.0,
     return out
 
 
+def _semi_labels(D_out, pred_nogt, semi_TH):
+    """The pseudo-labels of the semi-supervised term (utils/trainer.py:727-739, :1998-2010): the
+    generator's own argmax where the discriminator output exceeds ``semi_TH``, 255 (ignored) elsewhere.
+    Returns (labels | None when every entry is ignored, fraction kept)."""
+    mask = (D_out <= semi_TH).squeeze(1)
+    semi_gt = torch.argmax(pred_nogt.detach(), dim=1)
+    semi_gt[mask] = 255
+    ratio = 1.0 - float(mask.sum().item()) / float(mask.numel())
+    return (None if ratio == 0.0 else semi_gt), ratio
+
+
+def adversarial_cls_semi_step(g_params, d_params, batch_gt, batch_nogt, optimizer, optimizer_D, i_iter,
+                              semi_start, semi_TH, lambda_cls=1.0, lambda_adv=1e-3, lambda_semi=1.0,
+                              labels=None, generator=None, training=False):
+    """One iteration of ``run_training_semi`` (utils/trainer.py:635-794), optimizer calls included
+    (zero_grad :644-645, steps :793-794): ``adversarial_cls_step`` plus, once
+    ``i_iter > semi_start > 0``, CrossEntropyLoss(ignore_index=255) of the unlabelled logits against
+    their own argmax where D_out > semi_TH (:727-739)."""
+    optimizer.zero_grad(); optimizer_D.zero_grad()
+    pts, y = batch_gt
+    (pts_nogt,) = batch_nogt
+    _set_requires_grad(d_params, False)
+    pred, _, _ = P.pointnet_cls_forward(g_params, pts, training=training)     # :681
+    l_cls = F.cross_entropy(pred, y)
+    pred_gt_ls = F.log_softmax(pred, dim=1)                                   # :685
+    pred_nogt, _, _ = P.pointnet_cls_forward(g_params, pts_nogt, training=training)  # :702
+    pred_nogt_ls = F.log_softmax(pred_nogt, dim=1)                            # :704
+    D_out = D.deepconv_disc_forward(d_params, pred_nogt_ls)                   # :711
+    l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False))
+    loss = lambda_cls * l_cls + lambda_adv * l_adv
+    out = dict(l_cls=l_cls.item(), l_adv=l_adv.item(), l_semi=None)
+    if semi_start > 0 and i_iter > semi_start:                                # :727
+        semi_gt, _ = _semi_labels(D_out, pred_nogt, semi_TH)
+        if semi_gt is not None:
+            l_semi = F.cross_entropy(pred_nogt, semi_gt, ignore_index=255)    # semi_loss, train_classification.py:201
+            loss = loss + lambda_semi * l_semi
+            out["l_semi"] = l_semi.item()
+    loss.backward()                                                           # :760
+    _set_requires_grad(d_params, True)
+    D_out = D.deepconv_disc_forward(d_params, pred_gt_ls.detach())            # :773
+    lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator)
+    l_D_gt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5
+    l_D_gt.backward()
+    D_out = D.deepconv_disc_forward(d_params, pred_nogt_ls.detach())          # :787
+    lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator)
+    l_D_nogt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5
+    l_D_nogt.backward()
+    optimizer.step(); optimizer_D.step()                                      # :793-794
+    out.update(l_D_gt=l_D_gt.item(), l_D_nogt=l_D_nogt.item())
+    return out
+
+
+def adversarial_seg_semi_step(g_params, d_params, batch_gt, batch_nogt, optimizer, optimizer_D, i_iter,
+                              semi_start, semi_TH, lambda_seg=1.0, lambda_adv=1e-3, lambda_semi=1.0,
+                              labels=None, generator=None):
+    """One iteration of ``run_training_seg_semi`` (utils/trainer.py:1927-2061), optimizer calls
+    included: G = PointNetSeg, D = PointwiseDiscNet; the generator is stepped right after its backward
+    (:2023), the discriminator at the end (:2061)."""
+    optimizer.zero_grad(); optimizer_D.zero_grad()                            # :1937-1938
+    pts, cls, seg = batch_gt
+    pts_nogt, cls_nogt = batch_nogt
+    n_pts = pts.shape[1]
+    _set_requires_grad(d_params, False)
+    pred, _ = P.pointnet_seg_forward(g_params, pts, cls)                      # :1969
+    l_seg = F.cross_entropy(pred, seg)
+    pred_gt_softmax = F.softmax(pred, dim=1)                                  # :1972
+    pred_nogt, _ = P.pointnet_seg_forward(g_params, pts_nogt, cls_nogt)       # :1984
+    pred_nogt_softmax = F.log_softmax(pred_nogt, dim=1)                       # :1985
+    D_out = D.pointwise_disc_forward(d_params, pred_nogt_softmax, n_pts)      # :1987
+    l_adv = F.binary_cross_entropy_with_logits(D_out, make_D_label(D_out.shape, 1, False))
+    loss = lambda_seg * l_seg + lambda_adv * l_adv
+    out = dict(l_seg=l_seg.item(), l_adv=l_adv.item(), l_semi=None)
+    if semi_start > 0 and i_iter > semi_start:                                # :1999
+        semi_gt, _ = _semi_labels(D_out, pred_nogt, semi_TH)
+        if semi_gt is not None:
+            l_semi = F.cross_entropy(pred_nogt, semi_gt, ignore_index=255)
+            loss = loss + lambda_semi * l_semi
+            out["l_semi"] = l_semi.item()
+    loss.backward()
+    optimizer.step()                                                          # :2022-2023
+    _set_requires_grad(d_params, True)
+    D_out = D.pointwise_disc_forward(d_params, pred_gt_softmax.detach(), n_pts)      # :2032
+    lab = labels[0] if labels is not None else make_D_label(D_out.shape, 1, True, generator)
+    l_D_gt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5
+    l_D_gt.backward()
+    D_out = D.pointwise_disc_forward(d_params, pred_nogt_softmax.detach(), n_pts)    # :2047
+    lab = labels[1] if labels is not None else make_D_label(D_out.shape, 0, True, generator)
+    l_D_nogt = F.binary_cross_entropy_with_logits(D_out, lab) * 0.5
+    l_D_nogt.backward()
+    optimizer_D.step()                                                        # :2061
+    out.update(l_D_gt=l_D_gt.item(), l_D_nogt=l_D_nogt.item())
+    return out
+
+
+def adversarial_seg_dual_step(g_params, shared, shape, point, batch_gt, batch_nogt, optimizer,
+                              optimizer_D_shape, optimizer_D_point, lambda_seg=1.0, lambda_adv=1e-3,
+                              lambda_disc_shape=1.0, labels=None, generator=None):
+    """One iteration of ``run_training_seg_dual`` (utils/trainer.py:2150-2284), optimizer calls
+    included because they interleave with the passes: the generator steps right after its backward
+    (:2225), ``optimizer_D_point`` (pointDisc + sharedDisc, train_segmentation.py:395-411) steps
+    BEFORE the shape pass runs on the updated sharedDisc (:2273-2275), and -- as written --
+    ``optimizer_D_shape.zero_grad()`` is called twice while ``optimizer_D_point`` is never zeroed
+    (:2171-2172), so pointDisc's gradients accumulate over iterations and sharedDisc's point-phase
+    gradient is still there when ``optimizer_D_shape`` steps.
+
+    shared / shape / point: parameter dicts of BaseDiscNet / ShapeDiscNet / PointDiscNet."""
+    optimizer.zero_grad()                                                     # :2170
+    optimizer_D_shape.zero_grad()                                             # :2171
+    optimizer_D_shape.zero_grad()                                             # :2172
+    pts, cls, seg = batch_gt
+    pts_nogt, cls_nogt = batch_nogt
+    n_pts = pts.shape[1]
+    for params in (shared, shape, point):                                     # :2174-2179
+        _set_requires_grad(params, False)
+    pred, _ = P.pointnet_seg_forward(g_params, pts, cls)                      # :2191
+    l_seg = F.cross_entropy(pred, seg)
+    pred_gt_softmax = F.softmax(pred, dim=1)                                  # :2194
+    pred_nogt, _ = P.pointnet_seg_forward(g_params, pts_nogt, cls_nogt)       # :2206
+    pred_nogt_softmax = F.log_softmax(pred_nogt, dim=1)                       # :2207
+    D_point = D.point_disc_forward(point, D.base_disc_forward(shared, pred_nogt_softmax), n_pts)   # :2209-2210
+    l_adv = F.binary_cross_entropy_with_logits(D_point, make_D_label(D_point.shape, 1, False))
+    (lambda_seg * l_seg + lambda_adv * l_adv).backward()                      # :2222-2223
+    optimizer.step()                                                          # :2224
+    for params in (shared, shape, point):                                     # :2229-2234
+        _set_requires_grad(params, True)
+    D_point = D.point_disc_forward(point, D.base_disc_forward(shared, pred_gt_softmax.detach()), n_pts)
+    lab = labels[0] if labels is not None else make_D_label(D_point.shape, 1, True, generator)
+    l_D_point_gt = 0.5 * F.binary_cross_entropy_with_logits(D_point, lab)     # :2249
+    D_point = D.point_disc_forward(point, D.base_disc_forward(shared, pred_nogt_softmax.detach()), n_pts)
+    lab = labels[1] if labels is not None else make_D_label(D_point.shape, 0, True, generator)
+    l_D_point_nogt = 0.5 * F.binary_cross_entropy_with_logits(D_point, lab)   # :2265
+    (l_D_point_gt + l_D_point_nogt).backward()                                # :2273-2274
+    optimizer_D_point.step()                                                  # :2275
+    D_shape = D.shape_disc_forward(shape, D.base_disc_forward(shared, pred_gt_softmax.detach()))   # :2277-2278
+    cls_gt = cls.argmax(dim=2).squeeze(1)                                     # :2279
+    l_D_shape = F.cross_entropy(D_shape, cls_gt.long())                       # :2280
+    (lambda_disc_shape * l_D_shape).backward()                                # :2283-2284
+    optimizer_D_shape.step()                                                  # :2285
+    return dict(l_seg=l_seg.item(), l_adv=l_adv.item(), l_D_point=l_D_point_gt.item() + l_D_point_nogt.item(),
+                l_D_shape=l_D_shape.item())
+
+
 def leaf_params(sd):
     """Detach-clone a state dict into autograd leaves."""
     return {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
