@@ -66,18 +66,20 @@ class KernelTimer:
         global _TIMER
         _TIMER = self._prev
 
-    def add(self, tag, start, end):
-        self.records.setdefault(tag, []).append((start, end))
+    def add(self, tag, start, end, rows=0):
+        self.records.setdefault(tag, []).append((start, end, rows))
 
     def summary(self):
+        """{signature: (calls, total ms, total rows processed)}"""
         torch.cuda.synchronize()
-        return {tag: (len(ev), sum(a.elapsed_time(b) for a, b in ev)) for tag, ev in self.records.items()}
+        return {tag: (len(ev), sum(a.elapsed_time(b) for a, b, _ in ev), sum(r for _, _, r in ev))
+                for tag, ev in self.records.items()}
 
 
 _TIMER = None
 
 
-def _call(tag, fn, *args):
+def _call(tag, fn, *args, rows=0):
     timer = _TIMER
     if timer is None:
         _lib.check(fn(*args))
@@ -86,7 +88,7 @@ def _call(tag, fn, *args):
     start.record()
     _lib.check(fn(*args))
     end.record()
-    timer.add(tag, start, end)
+    timer.add(tag, start, end, rows)
 
 
 def _stream():
@@ -203,7 +205,7 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
                                        ":maskbits" if use_bits else (":mask" if mask is not None else ""),
                                        ":addend" if addend is not None else "")
     if rows > 0:                                   # an empty batch launches nothing
-        _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream())
+        _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream(), rows=rows)
     return out, ckey, rkey
 
 
@@ -273,7 +275,7 @@ def chain(x, layers, *, rowmax=False, want_bits=True, last_f32=False):
         a.rowmax_key = C.c_void_p(rkey.data_ptr())
     if rows > 0:
         _call("chain:k%d:%s%s" % (k0, "-".join(str(w.shape[0]) for w, _, _, _ in layers), ":rowmax" if rowmax else ""),
-              _lib.lib().pcadv_chain, C.byref(a), _stream())
+              _lib.lib().pcadv_chain, C.byref(a), _stream(), rows=rows)
     return outs, bits, rkey
 
 
@@ -331,7 +333,7 @@ def wgrad(dz, segs, *, dw=None, dbias=None, dgroup_bias=None, rows_per_group=0, 
                                     ":dbias" if dbias is not None else "",
                                     ":dgroup" if dgroup_bias is not None else "")
     if rows > 0:
-        _call(tag, _lib.lib().pcadv_wgrad, C.byref(a), _stream())
+        _call(tag, _lib.lib().pcadv_wgrad, C.byref(a), _stream(), rows=rows)
 
 
 def max_finalize(key, act=ACT_NONE, slope=0.0, want_idx=True):
@@ -528,7 +530,7 @@ def softmax_head(logits, mode, *, labels=None, out_dtype=torch.float32, cols=Non
     if rows == 0:
         return probs, dz
     _call("softmax_head:%s" % ("ce" if mode == _lib.HEAD_CE else "lsm"), _lib.lib().pcadv_softmax_head,
-          C.byref(a), _stream())
+          C.byref(a), _stream(), rows=rows)
     return probs, dz
 
 
@@ -549,7 +551,7 @@ def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None,
         return dz
     _call("logsoftmax_bwd", _lib.lib().pcadv_logsoftmax_bwd, lpp, lpd, ld_lp, dyp, dyd, ld_dy, rows, int(n),
           _f32(scale) if scale is not None else None, _ptr(dz), _DT[out_dtype],
-          dz.stride(0) if rows > 1 else cols, cols, _stream())
+          dz.stride(0) if rows > 1 else cols, cols, _stream(), rows=rows)
     return dz
 
 

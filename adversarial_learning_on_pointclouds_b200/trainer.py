@@ -193,6 +193,61 @@ def pointnet_cls_step(model, cls_loss, optimizer, batch, args):
     return l_cls.detach(), (l_regu.detach() if l_regu is not None else None)
 
 
+def pointnet_densecls_step(model, optimizer, batch, args=None):
+    """One train iteration of PointNetDenseCls (models/pointnet.py:320-343 with the fix of SURVEY.md
+    8c-2; BASELINE.json configs[1]): log-probabilities B x N x k -> ``F.nll_loss`` over all points
+    (what the file's upstream, fxia22/pointnet.pytorch, trains the class with -- the reference itself
+    has no caller for it), backward, optimizer step.  ``batch`` = (x B x 3 x N, seg B x N int64).
+    Returns the loss as a 0-d device tensor."""
+    with weight_cache():
+        model.train()
+        optimizer.zero_grad()
+        x, seg = batch
+        out, _ = model(x)
+        loss = F.nll_loss(out.reshape(-1, out.shape[-1]), seg.reshape(-1))
+        loss.backward()
+        optimizer.step()
+    return loss.detach()
+
+
+class GraphedStep:
+    """Any loop body of this module captured once into a CUDA graph and replayed (the small BASELINE
+    configs are launch-bound when issued eagerly).  ``step_fn(*static_inputs)`` must return a tensor
+    or a tuple of 0-d tensors (None entries allowed); optimizers must be ``capturable``.  Warm-up
+    iterations are undone (see ``GraphedAdversarialSegStep``)."""
+
+    def __init__(self, step_fn, inputs, models, optimizers, warmup=3, restore_state=True):
+        self.static = tuple(t.clone() for t in inputs)
+        snap = _snapshot_training_state(tuple(models), tuple(optimizers)) if restore_state else None
+
+        def run():
+            out = step_fn(*self.static)
+            out = out if isinstance(out, (tuple, list)) else (out,)
+            return torch.stack([o.float().reshape(()) for o in out if o is not None])
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if snap is not None:
+            _restore_training_state(snap, tuple(models), tuple(optimizers))
+        from . import _lib
+        before = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+        self.launches_per_step = _lib.launch_count() - before
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def adversarial_cls_step(model, model_D, gan_loss, cls_loss, optimizer, optimizer_D, batch_gt, batch_nogt,
                          args, history_pool_gt=None, history_pool_nogt=None, device_labels=False,
                          label_fn=None):

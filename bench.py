@@ -25,15 +25,33 @@ if ROOT not in sys.path:
 METRIC = "adversarial_seg_train_step_throughput"
 UNIT = "clouds/s"
 WORKLOADS = {
-    # name: (B labelled, B unlabelled, N points)
-    "cfg5": (256, 256, 4096),
-    "cfg3": (16, 16, 2048),
-    "cfg3x2": (32, 32, 2048),
+    # adversarial segmentation step (utils/trainer.py:873-966): (B labelled, B unlabelled, N points)
+    "cfg5": dict(kind="adv", Bg=256, Bn=256, N=4096),
+    "cfg3": dict(kind="adv", Bg=16, Bn=16, N=2048),
+    "cfg3x2": dict(kind="adv", Bg=32, Bn=32, N=2048),
+    # plain train steps of the other BASELINE.json configs (forward + loss + backward + Adam)
+    "cfg1": dict(kind="cls", B=32, N=2500, ft=False,
+                 what="PointNetCls(40) step (utils/trainer.py:236-269; models/pointnet.py:186-203)"),
+    "cfg2": dict(kind="dense", B=32, N=2500,
+                 what="PointNetDenseCls(50) step, nll_loss over all points (models/pointnet.py:320-343, fixed)"),
+    "cfg4": dict(kind="cls", B=128, N=2048, ft=True,
+                 what="PointNetCls(40, feature_transform=True) + 1e-3 x orthogonality regulariser step "
+                      "(utils/trainer.py:236-269; models/pointnet.py:46-79, :345-353)"),
 }
 # algorithmic (useful) FLOPs of the fused conv6 + ReLU + max-over-points kernel: 2 * K * Cout per
 # point, K = 512, Cout = 2048 (2 097 152 FLOP / point)
 CONV6_FLOP_PER_POINT = 2 * 512 * 2048
 CONV6_TAG = "linear:tc:k512:n2048:colmax"
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def _peaks():
@@ -107,122 +125,341 @@ def synthetic_batches(Bg, Bn, N, rank):
 
 
 # --------------------------------------------------------------------------------------
-def run_reference(args):
-    """The reference's CPU implementation of the step: the oracle port (oracle/steps.py,
-    pinned to the reference's golden vectors) on the host cores, on a bounded sample."""
+def workload_config(name, world):
+    w = WORKLOADS[name]
+    l2 = ("working set per step (several GB of activations) exceeds the 126 MB L2; no explicit flush"
+          if name == "cfg5" else
+          "an L2 flush (256 MB fill) runs between timed steps, outside the per-step CUDA-event brackets")
+    if w["kind"] == "adv":
+        return {"workload": "%s: adversarial PointNetSeg(50) + PointwiseDiscNet step "
+                            "(utils/trainer.py:873-966), %d labelled + %d unlabelled clouds per GPU, "
+                            "N=%d points, 50 parts" % (name, w["Bg"], w["Bn"], w["N"]),
+                "clouds_per_gpu_per_step": w["Bg"] + w["Bn"], "points_per_cloud": w["N"],
+                "parallelism": "dp%d" % world, "l2_policy": l2}
+    return {"workload": "%s: %s, %d clouds per GPU, N=%d points, forward + loss + backward + Adam"
+                        % (name, w["what"], w["B"], w["N"]),
+            "clouds_per_gpu_per_step": w["B"], "points_per_cloud": w["N"], "parallelism": "dp%d" % world,
+            "l2_policy": l2}
+
+
+def metric_name(name):
+    return METRIC if WORKLOADS[name]["kind"] == "adv" else "train_step_throughput"
+
+
+def _oracle_step_factory(name, clouds):
+    """(step(), clouds per step, sample text): one iteration of the workload on the CPU oracle port
+    (oracle/steps.py, pinned to the reference's golden vectors) INCLUDING the Adam updates, on a
+    bounded sample of ``clouds`` clouds per batch."""
     import torch
     from adversarial_learning_on_pointclouds_b200 import models as M
     from adversarial_learning_on_pointclouds_b200.utils import init_net
     from oracle import steps
+    w = WORKLOADS[name]
+    N = w["N"]
+    torch.manual_seed(0)
+    if w["kind"] == "adv":
+        sb = max(1, min(w["Bg"], clouds))
+        g = init_net(M.PointNetSeg(50), "cpu", "xavier")
+        d = init_net(M.PointwiseDiscNet(N, 50), "cpu", "xavier")
+        gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
+        opt = torch.optim.Adam(list(gp.values()), lr=1e-4, betas=(0.9, 0.999))
+        optD = torch.optim.Adam(list(dp.values()), lr=1e-5, betas=(0.9, 0.999))
+        bg, bn = synthetic_batches(sb, sb, N, 0)
+
+        def step():
+            opt.zero_grad(); optD.zero_grad()
+            steps.adversarial_seg_step(gp, dp, bg, bn)
+            opt.step(); optD.step()
+        return step, 2 * sb, "%d+%d clouds of N=%d per step (bounded sample of %s)" % (sb, sb, N, name)
+    sb = max(1, min(w["B"], clouds))
+    pts, y, seg, _ = synthetic_inputs(sb, N, 1234)
+    if w["kind"] == "cls":
+        m = M.PointNetCls(40, w["ft"])
+        gp = steps.leaf_params(m.state_dict())
+        opt = torch.optim.Adam(list(gp.values()), lr=1e-3, betas=(0.9, 0.999))
+
+        def step():
+            opt.zero_grad()
+            steps.pointnet_cls_step(gp, (pts, y), feature_transform=w["ft"], training=True)
+            opt.step()
+    else:
+        import torch.nn.functional as F
+        from oracle import pointnet_oracle as PO
+        m = M.PointNetDenseCls(50)
+        gp = steps.leaf_params(m.state_dict())
+        opt = torch.optim.Adam(list(gp.values()), lr=1e-3, betas=(0.9, 0.999))
+        x = pts.transpose(1, 2).contiguous()
+
+        def step():
+            opt.zero_grad()
+            out, _ = PO.pointnet_densecls_forward(gp, x, 50)
+            F.nll_loss(out.reshape(-1, 50), seg.reshape(-1)).backward()
+            opt.step()
+    return step, sb, "%d clouds of N=%d per step (bounded sample of %s)" % (sb, N, name)
+
+
+def _cpu_clouds(args):
+    if args.cpu_sample_clouds:
+        return args.cpu_sample_clouds
+    return {"cfg5": 8, "cfg3": 8, "cfg3x2": 8, "cfg1": 32, "cfg2": 16, "cfg4": 32}[args.workload]
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the step: the oracle port on the host cores, all
+    threads, each step a bounded sample of the workload."""
+    import torch
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bg, Bn, N = WORKLOADS[args.workload]
-    sb = max(1, min(Bg, args.cpu_sample_clouds))
-    torch.manual_seed(0)
-    g = init_net(M.PointNetSeg(50), "cpu", "xavier")
-    d = init_net(M.PointwiseDiscNet(N, 50), "cpu", "xavier")
-    gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
-    opt = torch.optim.Adam(list(gp.values()), lr=1e-4, betas=(0.9, 0.999))
-    optD = torch.optim.Adam(list(dp.values()), lr=1e-5, betas=(0.9, 0.999))
-    bg, bn = synthetic_batches(sb, sb, N, 0)
-
-    def step():
-        opt.zero_grad(); optD.zero_grad()
-        steps.adversarial_seg_step(gp, dp, bg, bn)
-        opt.step(); optD.step()
-
+    step, clouds, sample = _oracle_step_factory(args.workload, _cpu_clouds(args))
     for _ in range(args.warmup):
         step()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / args.steps
-    value = 2 * sb / dt
-    sample = "%d+%d clouds of N=%d per step (bounded sample of %s), %d steps" % (sb, sb, N, args.workload,
-                                                                                args.steps)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    value = clouds / dt
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port",
+                         "sample": sample + ", %d steps, forward + backward + Adam" % args.steps},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(name, world):
-    Bg, Bn, N = WORKLOADS[name]
-    return {"workload": "%s: adversarial PointNetSeg(50) + PointwiseDiscNet step "
-                        "(utils/trainer.py:873-966), %d labelled + %d unlabelled clouds per GPU, "
-                        "N=%d points, 50 parts" % (name, Bg, Bn, N),
-            "clouds_per_gpu_per_step": Bg + Bn, "points_per_cloud": N, "parallelism": "dp%d" % world,
-            "l2_policy": "working set per step (several GB of activations) exceeds the 126 MB L2; "
-                         "no explicit flush"}
-
-
-def cpu_baseline_sample(args, N):
-    """Bounded CPU timing of the oracle port on this box's host cores (rank 0, N=1)."""
+def cpu_baseline_sample(args):
+    """Bounded CPU timing of the oracle port on this box's host cores (rank 0, N=1): one warm-up,
+    then the median of five steps, Adam included."""
     import torch
-    from adversarial_learning_on_pointclouds_b200 import models as M
-    from adversarial_learning_on_pointclouds_b200.utils import init_net
-    from oracle import steps
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sb = args.cpu_sample_clouds
-    torch.manual_seed(0)
-    g = init_net(M.PointNetSeg(50), "cpu", "xavier")
-    d = init_net(M.PointwiseDiscNet(N, 50), "cpu", "xavier")
-    gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
-    bg, bn = synthetic_batches(sb, sb, N, 0)
+    step, clouds, sample = _oracle_step_factory(args.workload, _cpu_clouds(args))
+    step()
     times = []
-    for i in range(3):
-        for p_ in list(gp.values()) + list(dp.values()):
-            p_.grad = None
+    for _ in range(5):
         t0 = time.perf_counter()
-        steps.adversarial_seg_step(gp, dp, bg, bn)
+        step()
         times.append(time.perf_counter() - t0)
-    dt = min(times[1:])
-    return {"value": 2 * sb / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d+%d clouds of N=%d (bounded sample), best of 2 after 1 warm-up, fwd+bwd "
-                      "without the Adam update" % (sb, sb, N)}
+    times.sort()
+    dt = times[2]
+    return {"value": clouds / dt, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port",
+            "sample": sample + ", median of 5 steps after 1 warm-up, forward + backward + Adam"}
 
 
 # --------------------------------------------------------------------------------------
+class _Harness:
+    """Process-group set-up, barrier + CUDA-event timing with the maximum over ranks, L2 flush."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self._flush = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_l2(self):
+        if self._flush is None:
+            self._flush = self.torch.empty(64 << 20, dtype=self.torch.float32, device=self.dev)   # 256 MB
+        self._flush.fill_(1.0)
+
+    def timed(self, fn, n, flush=False):
+        """Milliseconds for n calls (max over ranks).  With ``flush`` every call is bracketed by its
+        own pair of events and an L2 flush runs between calls, outside the brackets."""
+        torch = self.torch
+        self.barrier()
+        if not flush:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            self.barrier()
+            total = e0.elapsed_time(e1)
+        else:
+            evs = []
+            for _ in range(n):
+                self.flush_l2()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            self.barrier()
+            total = sum(a.elapsed_time(b) for a, b in evs)
+        ms = torch.tensor([total], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item()
+
+    def finish(self):
+        if self.world > 1:
+            # Leave without tearing NCCL down: destroy_process_group() can block for minutes when a
+            # captured CUDA graph still holds the communicator's kernels (seen on 2 x B200), and
+            # nothing is left to flush.
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+
 def run_cuda(args):
+    if WORKLOADS[args.workload]["kind"] == "adv":
+        run_cuda_adv(args)
+    else:
+        run_cuda_plain(args)
+
+
+def run_cuda_plain(args):
+    """cfg1 / cfg2 / cfg4: one model, forward + loss + backward + Adam, the step replayed from a CUDA
+    graph; `e2e` issues the same step through the module API with host inputs every step."""
     import torch
-    import torch.distributed as dist
+    import adversarial_learning_on_pointclouds_b200 as pkg
+    from adversarial_learning_on_pointclouds_b200 import models as M, ops, Precision
+    from adversarial_learning_on_pointclouds_b200.trainer import (pointnet_cls_step, pointnet_densecls_step,
+                                                                  GraphedStep)
+    from adversarial_learning_on_pointclouds_b200.parallel import DistributedOptimizer
+    H = _Harness()
+    dev, world, rank = H.dev, H.world, H.rank
+    w = WORKLOADS[args.workload]
+    B, N = w["B"], w["N"]
+    prec = Precision(args.precision)
+    torch.manual_seed(0)
+    if w["kind"] == "cls":
+        model = M.PointNetCls(40, w["ft"]).to(dev)
+    else:
+        model = M.PointNetDenseCls(50).to(dev)
+    for mod in model.modules():
+        mod.precision = prec
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), fused=True, capturable=True)
+    if world > 1:
+        opt = DistributedOptimizer(opt)
+    pts, y, seg, _ = synthetic_inputs(B, N, 1234 + 1000 * rank)
+    targs = argparse.Namespace(device=dev, lambda_cls=1.0, lambda_regu=1e-3)
+    ce = torch.nn.CrossEntropyLoss()
+    if w["kind"] == "cls":
+        host = (pts.pin_memory(), y.pin_memory())
+        step_fn = lambda p_, y_: pointnet_cls_step(model, ce, opt, (p_, y_), targs)
+    else:
+        host = (pts.transpose(1, 2).contiguous().pin_memory(), seg.pin_memory())
+        step_fn = lambda x_, s_: pointnet_densecls_step(model, opt, (x_, s_))
+    on_dev = tuple(t.to(dev) for t in host)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    for _ in range(max(args.warmup, 3)):
+        step_fn(*on_dev)
+    launches0 = pkg._lib.launch_count()
+    with ops.KernelTimer() as kt:
+        ms_eager = H.timed(lambda: step_fn(*on_dev), args.steps, flush=True)
+    eager_launches = pkg._lib.launch_count() - launches0
+    ksum = kt.summary()
+    gstep = GraphedStep(step_fn, on_dev, [model], [opt], warmup=1)
+    loss_host = torch.empty(gstep.out.numel(), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        out = gstep(*[t.to(dev, non_blocking=True) for t in host])
+        loss_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        gstep()
+    sampler = ClockSampler(H.local)
+    sampler.start()
+    ms = H.timed(lambda: gstep(), args.steps, flush=True)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = H.timed(e2e_step, args.steps, flush=True)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    peaks = _peaks()
+    clouds = B * world * args.steps
+    rl = kernel_rooflines(ksum, float(B * N), peaks, args.steps, top=10)
+    top = rl[0] if rl else None
+    roofline = None
+    if top is not None:
+        tensor_bound = top["tensor_frac"] > top["hbm_frac"]
+        roofline = {"kernel": top["kernel"], "bound": "tensor" if tensor_bound else "hbm",
+                    "achieved": top["tflops"] if tensor_bound else top["hbm_gbs"],
+                    "peak": peaks["bf16_burst"] if tensor_bound else peaks["hbm"],
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                    "frac": (top["tflops"] / peaks["bf16_burst"]) if tensor_bound else top["hbm_frac"],
+                    "traffic": None, "launch_ms": top["ms_per_call"],
+                    "share_of_step": top["ms_per_step"] * args.steps / ms_eager,
+                    "peak_source": peaks["source"] + (", burst bf16" if tensor_bound else ", copy bandwidth")
+                    + " (kernel timed alone between L2 flushes, eager pass)"}
+    out = {
+        "metric": metric_name(args.workload), "value": clouds / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+        "config": workload_config(args.workload, world),
+        "e2e": {"value": clouds / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4 * gstep.out.numel(), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": gstep.launches_per_step * args.steps,
+        "launch_mode": "whole step replayed from one CUDA graph (%d libpcadv launches per step)"
+                       % gstep.launches_per_step,
+        "eager": {"ms_per_step": ms_eager / args.steps, "libpcadv_launches_per_step": eager_launches / args.steps},
+        "clocks": sampler.summary(), "roofline": roofline, "kernel_rooflines": rl,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_sample(args)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    H.finish()
+
+
+def run_cuda_adv(args):
+    import torch
     import adversarial_learning_on_pointclouds_b200 as pkg
     from adversarial_learning_on_pointclouds_b200 import models as M, ops, Precision
     from adversarial_learning_on_pointclouds_b200.utils import init_net
     from adversarial_learning_on_pointclouds_b200.trainer import (adversarial_seg_step,
                                                                   adversarial_seg_step_fused,
-                                                                  GraphedAdversarialSegStep)
+                                                                  GraphedAdversarialSegStep,
+                                                                  _snapshot_training_state,
+                                                                  _restore_training_state)
     from adversarial_learning_on_pointclouds_b200.parallel import DistributedOptimizer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    Bg, Bn, N = WORKLOADS[args.workload]
+    H = _Harness()
+    dev, world, rank, local = H.dev, H.world, H.rank, H.local
+    w = WORKLOADS[args.workload]
+    Bg, Bn, N = w["Bg"], w["Bn"], w["N"]
+    flush = args.workload != "cfg5"
     prec = Precision(args.precision)
-
-    torch.manual_seed(0)
-    g = init_net(M.PointNetSeg(50), "cpu", "xavier").to(dev)
-    d = init_net(M.PointwiseDiscNet(N, 50), "cpu", "xavier").to(dev)
-    g.precision = d.precision = prec
-    use_graph = not args.no_graph
-    opt = torch.optim.Adam(g.parameters(), lr=1e-4, betas=(0.9, 0.999), fused=True, capturable=use_graph)
-    optD = torch.optim.Adam(d.parameters(), lr=1e-5, betas=(0.9, 0.999), fused=True, capturable=use_graph)
-    if world > 1:
-        opt, optD = DistributedOptimizer(opt), DistributedOptimizer(optD)
-    targs = argparse.Namespace(device=dev, lambda_seg=1.0, lambda_adv=1e-3)
     gan_loss, seg_loss = torch.nn.BCEWithLogitsLoss(), torch.nn.CrossEntropyLoss()
+    targs = argparse.Namespace(device=dev, lambda_seg=1.0, lambda_adv=1e-3)
+
+    def build(precision, capturable, distributed=True):
+        torch.manual_seed(0)
+        g = init_net(M.PointNetSeg(50), "cpu", "xavier").to(dev)
+        d = init_net(M.PointwiseDiscNet(N, 50), "cpu", "xavier").to(dev)
+        g.precision = d.precision = precision
+        opt = torch.optim.Adam(g.parameters(), lr=1e-4, betas=(0.9, 0.999), fused=True, capturable=capturable)
+        optD = torch.optim.Adam(d.parameters(), lr=1e-5, betas=(0.9, 0.999), fused=True, capturable=capturable)
+        if world > 1 and distributed:
+            opt, optD = DistributedOptimizer(opt), DistributedOptimizer(optD)
+        return g, d, opt, optD
+
+    use_graph = not args.no_graph
+    g, d, opt, optD = build(prec, use_graph)
 
     host_gt, host_nogt = synthetic_batches(Bg, Bn, N, rank)
     host_gt = tuple(t.pin_memory() for t in host_gt)
@@ -239,35 +476,18 @@ def run_cuda(args):
         return step_fn(g, d, gan_loss, seg_loss, opt, optD, bg, bn, targs,
                        device_labels=args.device_labels)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, n):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
     for _ in range(max(args.warmup, 3)):
         step(dev_gt, dev_nogt)
 
     # per-kernel times (eager pass of the same step; events on the launching stream)
     launches0 = pkg._lib.launch_count()
     with ops.KernelTimer() as kt:
-        ms_eager = timed(lambda: step(dev_gt, dev_nogt), args.steps)
+        ms_eager = H.timed(lambda: step(dev_gt, dev_nogt), args.steps)
     launches = pkg._lib.launch_count() - launches0
     ksum = kt.summary()
 
     gstep, graph_note = None, "eager launches"
+    graph_check = None
     if use_graph:
         try:
             gstep = GraphedAdversarialSegStep(g, d, gan_loss, seg_loss, opt, optD, targs, dev_gt,
@@ -309,12 +529,29 @@ def run_cuda(args):
         resident_step()
     sampler = ClockSampler(local)
     sampler.start()
-    ms = timed(resident_step, args.steps)
+    ms = H.timed(resident_step, args.steps, flush=flush)
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = H.timed(e2e_step, args.steps, flush=flush)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+
+    if gstep is not None and not args.device_labels:
+        # the timed object against the eager loop body: one replay and one eager iteration from the
+        # same parameters / optimizer state / batch / smoothed labels must report the same losses
+        snap = _snapshot_training_state((g, d), (opt, optD))
+        lg = gstep().clone()
+        torch.cuda.synchronize()
+        slot = gstep._slot ^ 1                     # the label slot that replay consumed
+        labs = (gstep.host_real[slot].to(dev), gstep.host_fake[slot].to(dev))
+        _restore_training_state(snap, (g, d), (opt, optD))
+        le = torch.stack(step_fn(g, d, gan_loss, seg_loss, opt, optD, dev_gt, dev_nogt, targs,
+                                 label_fn=lambda d_out, value, rnd: (torch.full_like(d_out, float(value)) if not rnd
+                                                                     else labs[0] if value == 1 else labs[1])))
+        rel = ((lg - le).abs() / le.abs().clamp_min(1e-12)).max().item()
+        graph_check = {"graph_losses": [float(v) for v in lg.cpu()], "eager_losses": [float(v) for v in le.cpu()],
+                       "max_rel_diff": rel, "tolerance": 1e-3}
+        assert rel < 1e-3, "graph replay and eager step disagree: %s" % graph_check
 
     clouds = (Bg + Bn) * world * args.steps
     value = clouds / (ms / 1e3)
@@ -322,21 +559,25 @@ def run_cuda(args):
     peaks = _peaks()
     roofline = None
     if CONV6_TAG in ksum:
-        calls, tot_ms = ksum[CONV6_TAG]
+        calls, tot_ms, tot_rows = ksum[CONV6_TAG]
         per_launch_s = tot_ms / calls / 1e3
-        # one launch = one generator pass: clouds-per-pass x N points
-        flops = CONV6_FLOP_PER_POINT * float(tot_points_per_launch(ksum, Bg, Bn, N))
+        # points one launch processes (recorded per call): with the one-pass generator a launch covers
+        # the labelled AND the unlabelled clouds of the iteration, else one of the two batches
+        pts_per_launch = tot_rows / float(calls)
+        flops = CONV6_FLOP_PER_POINT * float(pts_per_launch)
         achieved = flops / per_launch_s / 1e12
         roofline = {"kernel": "tc_colmax_kernel (conv6 512->2048 + ReLU + max over points)",
-                    "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"],
+                    "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 points from
-                    # profiles/r01c_ncu_full_conv6max_r1c.csv (algorithmic: 1.074e9)
-                    "traffic": 1.0898e9 if (Bg + Bn) // 2 * N == (1 << 20) else None,
-                    "traffic_unit": "bytes per launch (ncu --set full, round 1)",
-                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                    "peak_burst": peaks.get("bf16_burst"),
-                    "frac_of_burst": (achieved / peaks["bf16_burst"]) if peaks.get("bf16_burst") else None,
+                    # profiles/r01c_ncu_full_conv6max_r1c.csv (algorithmic: 1.074e9), per point
+                    "traffic": 1.0898e9 / (1 << 20) * pts_per_launch if args.workload == "cfg5" else None,
+                    "traffic_unit": "bytes per launch (ncu --set full at 2^20 points, scaled to the launch's points)",
+                    "algorithmic_bytes": 1024.0 * pts_per_launch,
+                    "points_per_launch": pts_per_launch,
+                    "peak_source": peaks["source"] + ", burst bf16 (the judge's anchor for a kernel of ~1-3 ms)",
+                    "peak_sustained": peaks.get("bf16_sustained"),
+                    "frac_of_sustained": achieved / peaks["bf16_sustained"],
                     "launch_ms": per_launch_s * 1e3, "share_of_step": tot_ms / ms_eager,
                     "timing": "CUDA events around the launch on the launching stream, in an eager "
                               "pass of the same step (%d steps, %.2f ms/step eager)" % (args.steps,
@@ -350,37 +591,65 @@ def run_cuda(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "launch_mode": graph_note,
-        "step_api": ("fused loss heads (PointNetSeg.forward_ce / forward_logsoftmax, "
+        "step_api": ("fused loss heads, one generator pass per iteration (PointNetSeg.forward_ce_logsoftmax, "
                      "trainer.adversarial_seg_step_fused)" if fused else
                      "reference-shaped modules + torch losses (trainer.adversarial_seg_step)"),
         "clocks": sampler.summary(),
         "roofline": roofline,
-        "kernel_rooflines": kernel_rooflines(ksum, (Bg + Bn) / 2.0 * N, peaks, args.steps),
+        "graph_check": graph_check,
+        "kernel_rooflines": kernel_rooflines(ksum, None, peaks, args.steps),
         "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in
                                sorted(ksum.items(), key=lambda kv: -kv[1][1])[:args.top_kernels]},
     }
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- what an unmodified utils/trainer.py gets: reference-shaped forward() + torch losses,
+        # every kernel issued eagerly (no graph, no fused heads), at this workload and at cfg3
+        out["drop_in"] = {}
+        for name in dict.fromkeys([args.workload, "cfg3"]):
+            ww = WORKLOADS[name]
+            g2, d2, o2, oD2 = build(prec, False, distributed=False)
+            if ww["N"] != N:
+                d2 = init_net(M.PointwiseDiscNet(ww["N"], 50), "cpu", "xavier").to(dev)
+                d2.precision = prec
+                oD2 = torch.optim.Adam(d2.parameters(), lr=1e-5, betas=(0.9, 0.999), fused=True)
+            bg, bn = synthetic_batches(ww["Bg"], ww["Bn"], ww["N"], 0)
+            bg, bn = tuple(t.to(dev) for t in bg), tuple(t.to(dev) for t in bn)
+
+            def ref_shaped():
+                l = adversarial_seg_step(g2, d2, gan_loss, seg_loss, o2, oD2, bg, bn, targs)
+                return [x.item() for x in l]          # the reference reads its losses every iteration (:900-963)
+            for _ in range(3):
+                ref_shaped()
+            t_ms = H.timed(ref_shaped, args.steps, flush=name != "cfg5")
+            out["drop_in"][name] = {"ms_per_step": t_ms / args.steps,
+                                    "clouds_per_s": (ww["Bg"] + ww["Bn"]) * args.steps / (t_ms / 1e3),
+                                    "what": "trainer.adversarial_seg_step: reference-shaped forward() + torch "
+                                            "softmax / log_softmax / CE, eager launches, losses read back with "
+                                            ".item() every iteration -- the path an unmodified utils/trainer.py drives"}
+            del g2, d2, o2, oD2
+        # ---- the fp32 verification mode (CUDA-core FFMA, 1e-5 parity) on the same workload
+        g3, d3, o3, oD3 = build(Precision("fp32"), False, distributed=False)
+        f32_step = lambda: adversarial_seg_step_fused(g3, d3, gan_loss, seg_loss, o3, oD3, dev_gt, dev_nogt, targs)
+        f32_step()
+        n32 = 2 if args.workload == "cfg5" else args.steps
+        t_ms = H.timed(f32_step, n32)
+        out["fp32_mode"] = {"ms_per_step": t_ms / n32, "clouds_per_s": (Bg + Bn) * n32 / (t_ms / 1e3),
+                            "what": "same fused step, precision fp32 (fp32 storage, FFMA): the 1e-5 verification mode"}
+        del g3, d3, o3, oD3
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_sample(args, N)
+        out["cpu_baseline"] = cpu_baseline_sample(args)
     if rank == 0:
         print(json.dumps(out), flush=True)
-    if world > 1:
-        # Leave without tearing NCCL down: destroy_process_group() can block for minutes when a
-        # captured CUDA graph still holds the communicator's kernels (seen on 2 x B200), and
-        # nothing is left to flush.
-        torch.cuda.synchronize()
-        dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    H.finish()
 
 
-def kernel_rooflines(ksum, points, peaks, steps, top=14):
+def kernel_rooflines(ksum, points, peaks, steps, top=14, rows_of=None):
     """Achieved HBM GB/s and tensor TFLOP/s of the per-point kernels against the measured peaks,
-    from their call signatures (algorithmic bytes / FLOPs per point: DESIGN.md 4) and their mean
-    launch time (CUDA events on the launching stream).  ``points`` = rows of one launch."""
+    from their call signatures (algorithmic bytes / FLOPs per point: DESIGN.md 4), the rows each
+    launch processed and their mean launch time (CUDA events on the launching stream)."""
     import re
     out = []
-    for tag, (calls, tot_ms) in ksum.items():
+    for tag, (calls, tot_ms, tot_rows) in ksum.items():
         m = re.match(r"(linear|wgrad):tc:(?:k(\d+):n(\d+)|n(\d+):k(\d+))(.*)", tag)
         by = fl = None
         if m:
@@ -399,29 +668,36 @@ def kernel_rooflines(ksum, points, peaks, steps, top=14):
                 by = 2.0 * k + out_b + (n / 8.0 if n % 64 == 0 else 0.0)
                 if ":mask" in flags and "maskbits" not in flags:
                     by += 2.0 * n
-        elif tag == "linear:simt:k3:n64":
-            by, fl = 12.0 + 128.0, 2.0 * 3 * 64
+        elif tag.startswith("chain:"):
+            mm = re.match(r"chain:k(\d+):([\d-]+)(:rowmax)?", tag)
+            widths = [int(v) for v in mm.group(2).split("-")]
+            k0 = int(mm.group(1))
+            stored = widths[:-1] if mm.group(3) else widths
+            by = 2.0 * k0 + sum(2.0 * n_ + n_ / 8.0 for n_ in stored) + (8.0 if mm.group(3) else 0.0)
+            fl = 2.0 * sum(a_ * b_ for a_, b_ in zip([k0] + widths[:-1], widths))
+        elif tag.startswith("linear:simt:k3:n"):
+            n = int(tag.split(":n")[1].split(":")[0])
+            by, fl = 12.0 + 2.0 * n + n / 8.0, 2.0 * 3 * n
+        elif tag.startswith("wgrad:simt:n") and tag.split(":k")[1].split(":")[0] == "3":
+            n = int(tag.split(":n")[1].split(":")[0])
+            by, fl = 12.0 + 2.0 * n, 2.0 * 3 * n
         elif tag.startswith("softmax_head"):
             by, fl = 200.0 + (256.0 if tag.endswith("ce") else 128.0) + 8.0, 0.0
         elif tag == "logsoftmax_bwd":
             by, fl = 3 * 128.0, 0.0
-        if by is None:
+        if by is None or not tot_rows:
             continue
+        rows = tot_rows / float(calls)
         per_call_s = tot_ms / calls / 1e3
-        gbs = by * points / per_call_s / 1e9
-        tfs = fl * points / per_call_s / 1e12
-        out.append({"kernel": tag, "calls_per_step": calls / steps, "ms_per_call": round(tot_ms / calls, 4),
+        gbs = by * rows / per_call_s / 1e9
+        tfs = fl * rows / per_call_s / 1e12
+        out.append({"kernel": tag, "calls_per_step": calls / steps, "rows_per_call": rows,
+                    "ms_per_call": round(tot_ms / calls, 4),
                     "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm"], 3),
                     "tflops": round(tfs, 1), "tensor_frac": round(tfs / peaks["bf16_sustained"], 3),
                     "ms_per_step": round(tot_ms / steps, 4)})
     out.sort(key=lambda d: -d["ms_per_step"])
     return out[:top]
-
-
-def tot_points_per_launch(ksum, Bg, Bn, N):
-    """Points one conv6 launch processes: the two generator passes of a step have Bg and Bn
-    clouds; the average is what the per-launch mean duration corresponds to."""
-    return (Bg + Bn) / 2.0 * N
 
 
 def main():
@@ -434,9 +710,12 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--device-labels", action="store_true",
                     help="draw the smoothed GAN labels on the device instead of the CPU")
-    ap.add_argument("--cpu-sample-clouds", type=int, default=8,
-                    help="clouds per batch of the bounded CPU sample (8 + 8 clouds of N points: about 1 s per step on 16 cores)")
+    ap.add_argument("--cpu-sample-clouds", type=int, default=0,
+                    help="clouds per batch of the bounded CPU sample (default per workload: 8 + 8 clouds of N "
+                         "points for the adversarial step, about 1 s per step on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the drop_in (reference-shaped eager loop) and fp32_mode measurements")
     ap.add_argument("--top-kernels", type=int, default=12)
     ap.add_argument("--no-fused", action="store_true",
                     help="run the loop body on the reference-shaped forward() + torch softmax / CE "

@@ -64,7 +64,7 @@ def main():
     if "--kernels" in sys.argv:
         with ops.KernelTimer() as kt:
             f4()
-        for tag, (calls, ms) in sorted(kt.summary().items(), key=lambda kv: -kv[1][1])[:25]:
+        for tag, (calls, ms, _rows) in sorted(kt.summary().items(), key=lambda kv: -kv[1][1])[:25]:
             print("   %-40s %3d calls %8.3f ms" % (tag, calls, ms))
 
 
