@@ -296,6 +296,170 @@ def adversarial_cls_step(model, model_D, gan_loss, cls_loss, optimizer, optimize
     return l_cls.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
 
 
+def _semi_labels(D_out, pred_nogt, semi_TH):
+    """Pseudo-labels of the semi-supervised term (utils/trainer.py:727-739, :1998-2010): the
+    generator's own argmax where the discriminator output exceeds ``semi_TH``, 255 (ignored)
+    elsewhere.  Built on the device (the reference takes the argmax on the host and, in the
+    segmentation loop, indexes that host tensor with a device mask -- :2002 -- which only runs on a
+    CPU device).  Returns (labels | None when every entry is ignored, fraction kept); like the
+    reference (:733) this reads one number back from the device."""
+    mask = (D_out.detach() <= semi_TH).squeeze(1)
+    semi_gt = torch.argmax(pred_nogt.detach(), dim=1)
+    semi_gt = torch.where(mask, torch.full_like(semi_gt, 255), semi_gt)
+    ratio = 1.0 - float(mask.sum().item()) / float(mask.numel())
+    return (None if ratio == 0.0 else semi_gt), ratio
+
+
+def adversarial_cls_semi_step(model, model_D, gan_loss, cls_loss, semi_loss, optimizer, optimizer_D, batch_gt,
+                              batch_nogt, args, i_iter, history_pool_gt=None, history_pool_nogt=None,
+                              label_fn=None):
+    """One iteration of run_training_semi (utils/trainer.py:635-794): ``adversarial_cls_step`` plus,
+    once ``i_iter > args.semi_start > 0``, ``semi_loss`` (CrossEntropyLoss(ignore_index=255),
+    train_classification.py:201) of the unlabelled logits against their own argmax where
+    D_out > args.semi_TH.  Returns (l_cls, l_adv, l_semi | None, l_D)."""
+    pool_gt = history_pool_gt or ImagePool(0)
+    pool_nogt = history_pool_nogt or ImagePool(0)
+    label = label_fn or (lambda d_out, value, random: make_D_label(input=d_out, value=value, device=args.device,
+                                                                    random=random))
+    with weight_cache():
+        model.train(); model_D.train()
+        optimizer.zero_grad(); optimizer_D.zero_grad()                       # :644-645
+        for param in model_D.parameters():
+            param.requires_grad = False
+        pts, labels = batch_gt
+        pred, _, _ = model(pts)                                              # :681
+        l_cls = cls_loss(pred, labels)
+        pred_gt_ls = F.log_softmax(pred, dim=1)                              # :685
+        pts_nogt = batch_nogt[0] if isinstance(batch_nogt, (tuple, list)) else batch_nogt
+        pred_nogt, _, _ = model(pts_nogt)                                    # :702
+        pred_nogt_ls = F.log_softmax(pred_nogt, dim=1)                       # :704
+        D_out = model_D(pred_nogt_ls)                                        # :711
+        l_adv = gan_loss(D_out, label(D_out, 1, False))
+        loss = args.lambda_cls * l_cls + args.lambda_adv * l_adv
+        l_semi = None
+        if args.semi_start > 0 and i_iter > args.semi_start:                 # :727
+            semi_gt, _ = _semi_labels(D_out, pred_nogt, args.semi_TH)
+            if semi_gt is not None:
+                l_semi = semi_loss(pred_nogt, semi_gt)
+                loss = loss + args.lambda_semi * l_semi
+        loss.backward()                                                      # :760
+        _start_reduce(optimizer)
+        for param in model_D.parameters():
+            param.requires_grad = True
+        D_out = model_D(pool_gt.query(pred_gt_ls.detach()))                  # :771-773
+        loss_D_gt = gan_loss(D_out, label(D_out, 1, True)) * 0.5
+        loss_D_gt.backward()
+        D_out = model_D(pool_nogt.query(pred_nogt_ls.detach()))              # :785-787
+        loss_D_nogt = gan_loss(D_out, label(D_out, 0, True)) * 0.5
+        loss_D_nogt.backward()
+        optimizer.step()                                                     # :793-794
+        optimizer_D.step()
+    return l_cls.detach(), l_adv.detach(), (l_semi.detach() if l_semi is not None else None), \
+        (loss_D_gt + loss_D_nogt).detach()
+
+
+def adversarial_seg_semi_step(model, model_D, gan_loss, seg_loss, semi_loss, optimizer, optimizer_D, batch_gt,
+                              batch_nogt, args, i_iter, history_pool_gt=None, history_pool_nogt=None,
+                              label_fn=None):
+    """One iteration of run_training_seg_semi (utils/trainer.py:1927-2061): the adversarial
+    segmentation step with the semi-supervised term (:1998-2010); the generator is stepped right
+    after its backward (:2022-2023), the discriminator at the end (:2061).
+    Returns (l_seg, l_adv, l_semi | None, l_D)."""
+    pool_gt = history_pool_gt or ImagePool(0)
+    pool_nogt = history_pool_nogt or ImagePool(0)
+    label = label_fn or (lambda d_out, value, random: make_D_label(input=d_out, value=value, device=args.device,
+                                                                    random=random))
+    with weight_cache():
+        model.train(); model_D.train()
+        optimizer.zero_grad(); optimizer_D.zero_grad()                       # :1937-1938
+        for param in model_D.parameters():
+            param.requires_grad = False
+        pts, cls, seg = batch_gt
+        pred, _ = model(pts, cls)                                            # :1969
+        l_seg = seg_loss(pred, seg)
+        pred_gt_softmax = F.softmax(pred, dim=1)                             # :1972
+        pts_nogt, cls_nogt = batch_nogt
+        pred_nogt, _ = model(pts_nogt, cls_nogt)                             # :1984
+        pred_nogt_softmax = F.log_softmax(pred_nogt, dim=1)                  # :1985
+        D_out = model_D(pred_nogt_softmax)                                   # :1987
+        l_adv = gan_loss(D_out, label(D_out, 1, False))
+        loss = args.lambda_seg * l_seg + args.lambda_adv * l_adv
+        l_semi = None
+        if args.semi_start > 0 and i_iter > args.semi_start:                 # :1999
+            semi_gt, _ = _semi_labels(D_out, pred_nogt, args.semi_TH)
+            if semi_gt is not None:
+                l_semi = semi_loss(pred_nogt, semi_gt)
+                loss = loss + args.lambda_semi * l_semi
+        loss.backward()
+        optimizer.step()                                                     # :2022-2023
+        for param in model_D.parameters():
+            param.requires_grad = True
+        D_out = model_D(pool_gt.query(pred_gt_softmax.detach()))             # :2030-2032
+        loss_D_gt = gan_loss(D_out, label(D_out, 1, True)) * 0.5
+        loss_D_gt.backward()
+        D_out = model_D(pool_nogt.query(pred_nogt_softmax.detach()))         # :2045-2047
+        loss_D_nogt = gan_loss(D_out, label(D_out, 0, True)) * 0.5
+        loss_D_nogt.backward()
+        optimizer_D.step()                                                   # :2061
+    return l_seg.detach(), l_adv.detach(), (l_semi.detach() if l_semi is not None else None), \
+        (loss_D_gt + loss_D_nogt).detach()
+
+
+def adversarial_seg_dual_step(model, sharedDisc, shapeDisc, pointDisc, gan_point_loss, gan_shape_loss, seg_loss,
+                              optimizer, optimizer_D_shape, optimizer_D_point, batch_gt, batch_nogt, args,
+                              history_pool_gt=None, history_pool_nogt=None, label_fn=None):
+    """One iteration of run_training_seg_dual (utils/trainer.py:2150-2284): the generator against a
+    shared trunk (BaseDiscNet) with a per-point head (PointDiscNet, BCE-with-logits) and a shape
+    head (ShapeDiscNet, CrossEntropyLoss against the cloud's category).  The call sequence is the
+    reference's, quirks included: ``optimizer_D_shape.zero_grad()`` twice and ``optimizer_D_point``
+    never zeroed (:2171-2172), the generator stepped right after its backward (:2224), the point
+    optimizer stepped BEFORE the shape pass runs on the updated shared trunk (:2275-2278).
+    Returns (l_seg, l_adv, l_D_point, l_D_shape) as 0-d device tensors."""
+    pool_gt = history_pool_gt or ImagePool(0)
+    pool_nogt = history_pool_nogt or ImagePool(0)
+    label = label_fn or (lambda d_out, value, random: make_D_label(input=d_out, value=value, device=args.device,
+                                                                    random=random))
+    discs = (sharedDisc, shapeDisc, pointDisc)
+    model.train()
+    for m in discs:
+        m.train()
+    optimizer.zero_grad()                                                    # :2170
+    optimizer_D_shape.zero_grad()                                            # :2171
+    optimizer_D_shape.zero_grad()                                            # :2172
+    with weight_cache():
+        for m in discs:                                                      # :2174-2179
+            for param in m.parameters():
+                param.requires_grad = False
+        pts, cls, seg = batch_gt
+        pred, _ = model(pts, cls)                                            # :2191
+        l_seg = seg_loss(pred, seg)
+        pred_gt_softmax = F.softmax(pred, dim=1)                             # :2194
+        pts_nogt, cls_nogt = batch_nogt
+        pred_nogt, _ = model(pts_nogt, cls_nogt)                             # :2206
+        pred_nogt_softmax = F.log_softmax(pred_nogt, dim=1)                  # :2207
+        D_point = pointDisc(sharedDisc(pred_nogt_softmax))                   # :2209-2210
+        loss_adv = gan_point_loss(D_point, label(D_point, 1, False))
+        (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()    # :2222-2223
+        optimizer.step()                                                     # :2224
+        for m in discs:                                                      # :2229-2234
+            for param in m.parameters():
+                param.requires_grad = True
+        D_point = pointDisc(sharedDisc(pool_gt.query(pred_gt_softmax.detach())))       # :2237-2241
+        loss_D_point_gt = 0.5 * gan_point_loss(D_point, label(D_point, 1, True))
+        D_point = pointDisc(sharedDisc(pool_nogt.query(pred_nogt_softmax.detach())))   # :2253-2257
+        loss_D_point_nogt = 0.5 * gan_point_loss(D_point, label(D_point, 0, True))
+        (loss_D_point_gt + loss_D_point_nogt).backward()                     # :2273-2274
+    optimizer_D_point.step()                                                 # :2275
+    with weight_cache():                                                     # sharedDisc just changed
+        D_shape = shapeDisc(sharedDisc(pred_gt_softmax.detach()))            # :2277-2278
+        cls_gt = cls.argmax(dim=2).squeeze(1)                                # :2279
+        loss_D_shape = gan_shape_loss(D_shape, cls_gt.long())                # :2280
+        (args.lambda_disc_shape * loss_D_shape).backward()                   # :2283-2284
+    optimizer_D_shape.step()                                                 # :2285
+    return l_seg.detach(), loss_adv.detach(), (loss_D_point_gt + loss_D_point_nogt).detach(), \
+        loss_D_shape.detach()
+
+
 def _optimizers_of(opt):
     return getattr(opt, "optimizer", opt)
 

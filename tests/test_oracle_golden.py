@@ -232,3 +232,103 @@ def test_bench_synthetic_inputs_match_the_oracle_generator():
     from oracle.pointnet_oracle import synthetic_inputs
     for a, b in zip(bench.synthetic_inputs(3, 17, 1234), synthetic_inputs(3, 17, 1234)):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining live loop bodies (tests/golden/golden_steps.pt, made by make_golden_steps.py from the
+# reference's unmodified run_training_seg_dual / run_training_semi / run_training_seg_semi)
+import os
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def golden_steps():
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_steps.pt"), weights_only=False)
+
+
+def _check_after(params, expected, tol, tag):
+    for k, v in params.items():
+        assert_summary_close(v, expected[k], tol, tag + ":" + k)
+
+
+def dual_setup(N):
+    """The models of load_models("seg") / load_models("disc_dual") (utils/model_utils.py:81, :116-131)
+    from seed 0, in the golden script's construction order."""
+    torch.manual_seed(0)
+    g = init_net(M.PointNetSeg(50), "cpu", "xavier")
+    shared = init_net(M.BaseDiscNet(N, 50, 256), "cpu", "xavier")
+    shape = init_net(M.ShapeDiscNet(256, 16), "cpu", "xavier")
+    point = init_net(M.PointDiscNet(256, N), "cpu", "xavier")
+    return g, shared, shape, point
+
+
+def test_trainer_seg_dual_steps(golden_steps):
+    """oracle.steps.adversarial_seg_dual_step against two iterations of the reference's unmodified
+    run_training_seg_dual: three discriminators, optimizer_D_point never zeroed (utils/trainer.py:2171-2172),
+    sharedDisc stepped by both discriminator optimizers."""
+    G = golden_steps["dual"]
+    R = G["recipe"]
+    g, shared, shape, point = dual_setup(R["N"])
+    gp, sp, hp, pp = (steps.leaf_params(m.state_dict()) for m in (g, shared, shape, point))
+    opt = torch.optim.Adam(list(gp.values()), lr=R["lr_g"], betas=(0.9, 0.999))
+    opt_shape = torch.optim.SGD(list(hp.values()) + list(sp.values()), lr=R["lr_d"])
+    opt_point = torch.optim.SGD(list(pp.values()) + list(sp.values()), lr=R["lr_d"])
+    torch.manual_seed(R["label_seed"])
+    for it in range(R["iters"]):
+        pts, _, seg, cls = inputs(R["B"], R["N"], R["seed"] + it)
+        pts2, _, _, cls2 = inputs(R["B"], R["N"], R["seed2"] + it)
+        steps.adversarial_seg_dual_step(gp, sp, hp, pp, (pts, cls, seg), (pts2, cls2), opt, opt_shape, opt_point,
+                                        lambda_adv=R["lambda_adv"])
+    _check_after(gp, G["g"], 1e-6, "g")
+    _check_after(sp, G["shared"], 1e-6, "shared")
+    _check_after(hp, G["shape"], 1e-6, "shape")
+    _check_after(pp, G["point"], 1e-6, "point")
+
+
+def test_trainer_cls_semi_steps(golden_steps):
+    """oracle.steps.adversarial_cls_semi_step against three iterations of the reference's unmodified
+    run_training_semi (the third one with the semi-supervised term, utils/trainer.py:727-739)."""
+    G = golden_steps["cls_semi"]
+    R = G["recipe"]
+    torch.manual_seed(0)
+    g = M.PointNetCls(40, False)
+    d = init_net(M.DeepConvDiscNet(40, 1), "cpu", "xavier")
+    gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
+    opt = torch.optim.Adam(list(gp.values()), lr=1e-4, betas=(0.9, 0.999))
+    optD = torch.optim.Adam(list(dp.values()), lr=1e-5, betas=(0.9, 0.999))
+    torch.manual_seed(R["label_seed"])
+    saw_semi = False
+    for it in range(R["iters"]):
+        pts, y, _, _ = inputs(R["B"], R["N"], R["seed"] + it)
+        pts2 = inputs(R["B"], R["N"], R["seed2"] + it)[0]
+        r = steps.adversarial_cls_semi_step(gp, dp, (pts, y), (pts2,), opt, optD, it, R["semi_start"], R["semi_TH"])
+        saw_semi |= r["l_semi"] is not None
+    assert saw_semi
+    _check_after(gp, G["g"], 1e-6, "g")
+    _check_after(dp, G["d"], 1e-6, "d")
+
+
+def test_trainer_seg_semi_steps(golden_steps):
+    """oracle.steps.adversarial_seg_semi_step against three iterations of the reference's unmodified
+    run_training_seg_semi (utils/trainer.py:1903-2121; its semi branch runs on the CPU only: it
+    indexes a CPU tensor with a device mask, :2002)."""
+    G = golden_steps["seg_semi"]
+    R = G["recipe"]
+    torch.manual_seed(0)
+    g = init_net(M.PointNetSeg(50), "cpu", "xavier")
+    d = init_net(M.PointwiseDiscNet(R["N"], 50), "cpu", "xavier")
+    gp, dp = steps.leaf_params(g.state_dict()), steps.leaf_params(d.state_dict())
+    opt = torch.optim.Adam(list(gp.values()), lr=1e-4, betas=(0.9, 0.999))
+    optD = torch.optim.Adam(list(dp.values()), lr=1e-5, betas=(0.9, 0.999))
+    torch.manual_seed(R["label_seed"])
+    saw_semi = False
+    for it in range(R["iters"]):
+        pts, _, seg, cls = inputs(R["B"], R["N"], R["seed"] + it)
+        pts2, _, _, cls2 = inputs(R["B"], R["N"], R["seed2"] + it)
+        r = steps.adversarial_seg_semi_step(gp, dp, (pts, cls, seg), (pts2, cls2), opt, optD, it, R["semi_start"],
+                                            R["semi_TH"])
+        saw_semi |= r["l_semi"] is not None
+    assert saw_semi
+    _check_after(gp, G["g"], 1e-6, "g")
+    _check_after(dp, G["d"], 1e-6, "d")
