@@ -83,6 +83,7 @@ class ChainArgs(C.Structure):
 
 
 HEAD_CE, HEAD_LSM = 0, 1
+WS_MAXPOOL_BWD_INPLACE, WS_AMAX_SCALE = 0, 1
 
 # every symbol include/pcadv.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -126,6 +127,16 @@ SYMBOLS = {
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcadv_part_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcadv_query_workspace": (C.c_longlong, [C.c_int32, C.c_int64, C.c_int64, C.c_int32]),
+    "pcadv_jitter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_ulonglong,
+                               C.c_ulonglong, C.c_void_p]),
+    "pcadv_bn_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcadv_bn_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "pcadv_bn_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                               C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pcadv_transpose": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "pcadv_version": (C.c_int, []),

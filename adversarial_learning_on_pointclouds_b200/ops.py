@@ -381,7 +381,8 @@ def maxpool_bwd(dg, gval, idx, x, w, rows_per_group, *, act=ACT_NONE, slope=0.0,
     if dz_inout is not None:
         a.dz_inout, a.ld_dz, a.dz_dtype = _mat(dz_inout)
         a.prev_act, a.prev_slope = prev_act, float(prev_slope)
-        ws = torch.empty((groups * (int(rows_per_group) + 3 * n),), dtype=torch.int32, device=dg.device)
+        ws_bytes = query_workspace(_lib.WS_MAXPOOL_BWD_INPLACE, groups, rows_per_group, n)
+        ws = torch.empty((ws_bytes // 4,), dtype=torch.int32, device=dg.device)
         a.workspace = _ptr(ws)
     a.scale = _f32(scale) if scale is not None else None
     _call("maxpool_bwd:n%d:k%d" % (n, a.k), _lib.lib().pcadv_maxpool_bwd, C.byref(a), _stream())
@@ -612,6 +613,74 @@ def ortho_reg_bwd(diff, trans, norms, dloss):
     _call("ortho_reg_bwd:d%d" % d, _lib.lib().pcadv_ortho_reg_bwd, _f32c(diff), _f32c(trans), _f32c(norms),
           _f32c(dloss.reshape(1)), B, d, _f32c(dT), _stream())
     return dT
+
+
+def query_workspace(op, groups=0, rows_per_group=0, n=0):
+    """Bytes of caller-owned scratch an entry point wants: see ``pcadv_query_workspace``."""
+    v = int(_lib.load().pcadv_query_workspace(int(op), int(groups), int(rows_per_group), int(n)))
+    if v < 0:
+        raise _lib.PcadvError(_lib.load().pcadv_last_error().decode())
+    return v
+
+
+def jitter(pts, sigma=0.01, clip=0.05, seed=0, offset=0, out=None):
+    """pts + clip(sigma * N(0, 1), -clip, clip) on the device (dataset/modelNetData.py:80-91): see
+    ``pcadv_jitter``.  pts: contiguous fp32 CUDA tensor (any shape); ``out`` may be pts itself."""
+    if pts.dtype != torch.float32 or not pts.is_contiguous() or not pts.is_cuda:
+        raise ValueError("jitter expects a contiguous fp32 CUDA tensor")
+    if clip <= 0:
+        raise ValueError("clip must be positive (modelNetData.py:88)")
+    out = torch.empty_like(pts) if out is None else out
+    if pts.numel():
+        _call("jitter", _lib.lib().pcadv_jitter, _ptr(pts), _ptr(out), pts.numel(), float(sigma), float(clip),
+              int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _stream())
+    return out
+
+
+def bn_shape_ok(C):
+    g = C // 8
+    return C > 0 and C % 8 == 0 and g <= 256 and 256 % g == 0
+
+
+def bn_stats(x, eps=1e-5, momentum=0.1, running_mean=None, running_var=None):
+    """(mean [C], rstd [C]) of the rows of x [rows, C]; updates the running statistics when given:
+    see ``pcadv_bn_stats``."""
+    p, ld, dt = _mat(x)
+    rows, Cn = x.shape
+    ws = torch.zeros(2 * Cn, dtype=torch.float32, device=x.device)
+    mean = torch.empty(Cn, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(Cn, dtype=torch.float32, device=x.device)
+    _call("bn_stats:c%d" % Cn, _lib.lib().pcadv_bn_stats, p, dt, ld, rows, Cn, float(eps), float(momentum), _ptr(ws),
+          _ptr(mean), _ptr(rstd), _f32(running_mean) if running_mean is not None else None,
+          _f32(running_var) if running_var is not None else None, _stream(), rows=rows)
+    return mean, rstd
+
+
+def bn_apply(x, mean, rstd, gamma=None, beta=None, act=ACT_NONE, out_dtype=None):
+    p, ld, dt = _mat(x)
+    rows, Cn = x.shape
+    y = torch.empty((rows, Cn), dtype=out_dtype or x.dtype, device=x.device)
+    if rows:
+        _call("bn_apply:c%d" % Cn, _lib.lib().pcadv_bn_apply, p, dt, ld, rows, Cn, _f32(mean, Cn), _f32(rstd, Cn),
+              _f32(gamma, Cn) if gamma is not None else None, _f32(beta, Cn) if beta is not None else None, act,
+              _ptr(y), _DT[y.dtype], Cn, _stream(), rows=rows)
+    return y
+
+
+def bn_bwd(x, dy, mean, rstd, gamma=None, y=None, want_dx=True):
+    """(dx | None, dgamma [C], dbeta [C]): see ``pcadv_bn_bwd``; ``y`` = the ReLU'd output when the
+    layer has the fused ReLU."""
+    p, ld, dt = _mat(x)
+    gp, gld, gdt = _mat(dy)
+    rows, Cn = x.shape
+    yp, yld, ydt = _mat(y) if y is not None else (C.c_void_p(0), 0, F32)
+    dgamma = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(Cn, dtype=torch.float32, device=x.device)
+    dx = torch.empty((rows, Cn), dtype=dy.dtype, device=x.device) if want_dx else None
+    _call("bn_bwd:c%d" % Cn, _lib.lib().pcadv_bn_bwd, p, dt, ld, gp, gdt, gld, yp, ydt, yld, rows, Cn, _f32(mean, Cn),
+          _f32(rstd, Cn), _f32(gamma, Cn) if gamma is not None else None, _ptr(dgamma), _ptr(dbeta), _ptr(dx),
+          _DT[dx.dtype] if dx is not None else F32, Cn, _stream(), rows=rows)
+    return dx, dgamma, dbeta
 
 
 def part_counts(labels, logits=None, pred=None, want_pred=False):

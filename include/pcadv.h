@@ -368,6 +368,50 @@ int pcadv_part_iou(const int32_t* counts, const float* onehot, int64_t ld_onehot
                    const int32_t* part_begin, int32_t groups, int32_t C, double* iou, int32_t* cat,
                    void* stream);
 
+/*
+ * Scratch sizes (lower face): bytes of the caller-owned workspace an entry point wants
+ * for the given shape, or -1 (and pcadv_last_error) for an unknown op.
+ *   PCADV_WS_MAXPOOL_BWD_INPLACE  pcadv_maxbwd_args.workspace when dz_inout is set
+ *   PCADV_WS_AMAX_SCALE           pcadv_amax_scale's workspace (zero-filled by the caller)
+ */
+enum { PCADV_WS_MAXPOOL_BWD_INPLACE = 0, PCADV_WS_AMAX_SCALE = 1 };
+long long pcadv_query_workspace(int32_t op, int64_t groups, int64_t rows_per_group, int32_t n);
+
+/*
+ * On-device point jitter -- jitter_point_cloud of dataset/modelNetData.py:80-91:
+ *   dst[i] = src[i] + clamp(sigma * z_i, -clip, clip),  z_i ~ N(0, 1)
+ * over `count` floats (N x 3 coordinates).  z comes from Philox-4x32-10 keyed by `seed`: element i
+ * uses normal (i & 3) of counter (offset + (i >> 2)), Box-Muller on the 24-bit uniform pairs, so a
+ * (seed, offset) pair reproduces the same jitter on any launch geometry.  numpy's generator (the
+ * reference draws np.random.randn on the host) cannot be reproduced; the distribution is the contract.
+ * src == dst is allowed.
+ */
+int pcadv_jitter(const float* src, float* dst, int64_t count, float sigma, float clip,
+                 unsigned long long seed, unsigned long long offset, void* stream);
+
+/*
+ * OPTIONAL BatchNorm over point-major rows [rows, C] (C in {8, 16, ..., 2048}, a power of two).  The
+ * reference has NO BatchNorm (commented out at models/pointnet.py:100-103) -- this is
+ * the default-off layer BASELINE.json's north_star words, checked against torch.nn.BatchNorm1d only.
+ *   pcadv_bn_stats: per-channel batch mean and 1 / sqrt(var + eps) (biased variance), optionally the
+ *                   running statistics update of nn.BatchNorm1d (momentum, unbiased variance).
+ *                   workspace: 2 * C floats, zero-filled by the caller.
+ *   pcadv_bn_apply: y = act((x - mean) * rstd * gamma + beta), act in {NONE, RELU}; gamma / beta nullable.
+ *   pcadv_bn_bwd:   dbeta[c] += sum_r dy', dgamma[c] += sum_r dy' * xhat (caller zero-fills both),
+ *                   dx = gamma * rstd * (dy' - dbeta / rows - xhat * dgamma / rows)  (dx nullable);
+ *                   dy' = dy * [y > 0] when y (the ReLU'd output) is given, else dy.
+ */
+int pcadv_bn_stats(const void* x, int32_t x_dtype, int64_t ld_x, int64_t rows, int32_t C, float eps,
+                   float momentum, float* workspace, float* mean, float* rstd, float* running_mean,
+                   float* running_var, void* stream);
+int pcadv_bn_apply(const void* x, int32_t x_dtype, int64_t ld_x, int64_t rows, int32_t C, const float* mean,
+                   const float* rstd, const float* gamma, const float* beta, int32_t act, void* y,
+                   int32_t y_dtype, int64_t ld_y, void* stream);
+int pcadv_bn_bwd(const void* x, int32_t x_dtype, int64_t ld_x, const void* dy, int32_t dy_dtype, int64_t ld_dy,
+                 const void* y, int32_t y_dtype, int64_t ld_y, int64_t rows, int32_t C, const float* mean,
+                 const float* rstd, const float* gamma, float* dgamma, float* dbeta, void* dx, int32_t dx_dtype,
+                 int64_t ld_dx, void* stream);
+
 /* dst[c, r] = src[r, c] with conversion: builds the [k, n] copy of a weight
  * matrix that dgrad consumes. */
 int pcadv_transpose(const void* src, int32_t src_dtype, int64_t ld_src, int32_t rows, int32_t cols,
