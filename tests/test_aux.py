@@ -60,7 +60,7 @@ def test_jitter_kernel_matches_oracle_stream():
 @gpu
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("rows,C,dtype", [(1000, 64, torch.float32), (4097, 128, torch.float16), (333, 1024, torch.float32),
-                                           (5000, 8, torch.float32), (2, 256, torch.float32)])
+                                           (5000, 8, torch.float32), (16, 256, torch.float32)])
 def test_batchnorm_rows_matches_torch(rows, C, dtype, relu):
     """The optional BatchNorm layer against torch.nn.BatchNorm1d (+ ReLU): output, running statistics,
     input / weight / bias gradients, train and eval mode.  A large common offset checks the pivoted
