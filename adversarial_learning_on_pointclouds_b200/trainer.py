@@ -581,6 +581,15 @@ class GraphedAdversarialSegStep:
     # ---- input pipeline: the next batch's host -> device copy runs on a
     # copy stream under the current step; the step then moves it into the graph's static buffers
     # with a device-to-device copy
+    def set_jitter(self, sigma=0.01, clip=0.05, seed=0):
+        """Augment every prefetched batch on the device: the point coordinates of
+        both batches get ``clip(sigma * N(0, 1), -clip, clip)`` added on the copy stream, right behind
+        their host -> device copy -- jitter_point_cloud of dataset/modelNetData.py:80-91, which the
+        reference applies per cloud on the host inside the DataLoader workers.  The counter-based
+        stream advances with every batch, so a (seed, batch number) pair is reproducible."""
+        self._jitter = (float(sigma), float(clip), int(seed))
+        self._jitter_offset = 0
+
     def prefetch(self, batch_gt, batch_nogt):
         """Start copying the NEXT step's (pinned) host batch to device staging buffers."""
         if not hasattr(self, "_copy_stream"):
@@ -595,6 +604,12 @@ class GraphedAdversarialSegStep:
         with torch.cuda.stream(cs):
             for dst, src in zip(self._stage_gt + self._stage_nogt, tuple(batch_gt) + tuple(batch_nogt)):
                 dst.copy_(src, non_blocking=True)
+            if getattr(self, "_jitter", None) is not None:
+                from . import ops
+                sigma, clip, seed = self._jitter
+                for pts in (self._stage_gt[0], self._stage_nogt[0]):
+                    ops.jitter(pts, sigma, clip, seed, offset=self._jitter_offset, out=pts)
+                    self._jitter_offset += (pts.numel() + 3) // 4
             self._staged.record(cs)
 
     def step_prefetched(self):

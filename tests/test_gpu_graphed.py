@@ -255,6 +255,41 @@ def test_fused_ce_head_ignores_labels_like_cross_entropy(mode):
         assert rel_err(v.grad, ref[k]) < max(20 * tol, 2e-3 if mode != "fp32" else 0), k
 
 
+def test_prefetch_pipeline_delivers_the_batch_with_device_jitter():
+    """The input pipeline of the graphed step: what ``prefetch`` +
+    ``step_prefetched`` put into the graph's static buffers is the pinned host batch -- bit for bit
+    without augmentation, and the oracle's jitter stream of it (dataset/modelNetData.py:80-91) with
+    ``set_jitter``; labels and one-hots are never touched."""
+    from oracle import jitter_oracle as JO
+    B, N = 2, 256
+    g, d = _models(N, "fp16")
+    g.to(DEV); d.to(DEV)
+    opt, optD = _adam(g, d, True)
+    targs = argparse.Namespace(device=DEV, lambda_seg=1.0, lambda_adv=1e-3)
+    batches = _batches(B, N, 3)
+    pinned = [tuple(tuple(t.pin_memory() for t in part) for part in b) for b in batches]
+    first = tuple(tuple(t.to(DEV) for t in part) for part in batches[0])
+    gstep = GraphedAdversarialSegStep(g, d, torch.nn.BCEWithLogitsLoss(), torch.nn.CrossEntropyLoss(), opt, optD,
+                                      targs, first[0], first[1], warmup=1, fused=True)
+    gstep.prefetch(*pinned[1])
+    gstep.step_prefetched()
+    torch.cuda.synchronize()
+    for dst, src in zip(gstep.static_gt + gstep.static_nogt, batches[1][0] + batches[1][1]):
+        assert torch.equal(dst.cpu(), src)
+    gstep.set_jitter(sigma=0.01, clip=0.05, seed=77)
+    gstep.prefetch(*pinned[2])
+    losses = gstep.step_prefetched()
+    torch.cuda.synchronize()
+    assert torch.isfinite(losses).all()
+    (pts, cls, seg), (pts2, cls2) = batches[2]
+    want_gt = JO.jitter(pts.numpy(), 0.01, 0.05, seed=77, offset=0)
+    want_nogt = JO.jitter(pts2.numpy(), 0.01, 0.05, seed=77, offset=(pts.numel() + 3) // 4)
+    assert (gstep.static_gt[0].cpu() - torch.from_numpy(want_gt)).abs().max().item() < 2e-7
+    assert (gstep.static_nogt[0].cpu() - torch.from_numpy(want_nogt)).abs().max().item() < 2e-7
+    assert torch.equal(gstep.static_gt[1].cpu(), cls) and torch.equal(gstep.static_gt[2].cpu(), seg)
+    assert torch.equal(gstep.static_nogt[1].cpu(), cls2)
+
+
 def test_data_parallel_graphed_step_two_ranks():
     """2 ranks, NCCL all-reduce captured inside the graph (tests/dist_graph_check.py): replicas stay
     identical and equal the 1-rank global-batch step.  Needs two GPUs."""
