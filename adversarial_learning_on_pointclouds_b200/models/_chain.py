@@ -77,8 +77,12 @@ class weight_cache:
 
 
 def _wkey(kind, prec, tensors, extra):
-    return (kind, prec.name, tuple((t.data_ptr(), tuple(t.shape), t.stride(), t._version) for t in tensors),
-            tuple(extra))
+    # The stream is part of the key: an engine copy built on one stream must not be picked up by
+    # work issued on another one without an event in between (the step functions run the
+    # discriminator phase on a second stream, trainer.py); each stream builds its own copy.
+    stream = torch.cuda.current_stream().cuda_stream if tensors and tensors[0].is_cuda else 0
+    return (kind, prec.name, stream,
+            tuple((t.data_ptr(), tuple(t.shape), t.stride(), t._version) for t in tensors), tuple(extra))
 
 
 def compute_weight(prec, w32, k_list, n):

@@ -8,6 +8,8 @@ data-parallel launcher can call one iteration.  Losses come back as device
 tensors: the caller decides when to synchronise (the reference calls ``.item()``
 four times per iteration, :900, :925, :948, :963).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -103,7 +105,7 @@ def _start_reduce(optimizer):
 
 def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, batch_gt,
                                 batch_nogt, args, history_pool_gt=None, history_pool_nogt=None,
-                                device_labels=False, label_fn=None, one_pass=None):
+                                device_labels=False, label_fn=None, one_pass=None, overlap_d=None):
     """The same iteration (utils/trainer.py:873-966) through the generator's fused loss heads
     (SURVEY.md 8f rank 1): ``CrossEntropyLoss`` + ``softmax`` of the labelled pass and
     ``log_softmax`` of the unlabelled pass are one kernel each over the logits, and the
@@ -114,7 +116,10 @@ def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, o
     ``one_pass`` (default: when the loss weights allow it): the two generator passes of the
     iteration run as ONE pass over the labelled + unlabelled clouds (``forward_ce_logsoftmax``):
     clouds are independent through the network, so the sums are the same, with half the launches and
-    no gradient accumulation between two backward passes."""
+    no gradient accumulation between two backward passes.
+
+    ``overlap_d`` (default: inside a CUDA-graph capture): the discriminator phase is issued on a
+    second stream, concurrently with the generator's backward."""
     if not isinstance(seg_loss, torch.nn.CrossEntropyLoss) or seg_loss.weight is not None or \
             seg_loss.reduction != "mean" or seg_loss.label_smoothing != 0.0:
         raise ValueError("the fused step implements nn.CrossEntropyLoss() with default arguments")
@@ -154,21 +159,55 @@ def _adversarial_seg_step_fused(model, model_D, gan_loss, seg_loss, optimizer, o
         pred_nogt_softmax, _ = model.forward_logsoftmax(pts_nogt, cls_nogt)   # :913-914
     D_out = model_D(pred_nogt_softmax)
     loss_adv = gan_loss(D_out, label(D_out, gt_label, False))
-    (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()
-    _start_reduce(optimizer)       # G's gradients are final: their all-reduce runs under the D phase
 
-    for param in model_D.parameters():
-        param.requires_grad = True
-    D_out = model_D(pool_gt.query(pred_gt_softmax.detach()))
-    loss_D_gt = gan_loss(D_out, label(D_out, gt_label, True)) * 0.5
-    loss_D_gt.backward()
-    D_out = model_D(pool_nogt.query(pred_nogt_softmax.detach()))
-    loss_D_nogt = gan_loss(D_out, label(D_out, nogt_label, True)) * 0.5
-    loss_D_nogt.backward()
+    def train_D():                                                           # :931-963
+        for param in model_D.parameters():
+            param.requires_grad = True
+        D_gt = model_D(pool_gt.query(pred_gt_softmax.detach()))
+        l_gt = gan_loss(D_gt, label(D_gt, gt_label, True)) * 0.5
+        l_gt.backward()
+        D_nogt = model_D(pool_nogt.query(pred_nogt_softmax.detach()))
+        l_nogt = gan_loss(D_nogt, label(D_nogt, nogt_label, True)) * 0.5
+        l_nogt.backward()
+        return l_gt, l_nogt
+
+    if overlap_d is None:
+        overlap_d = _OVERLAP_D and torch.cuda.is_current_stream_capturing()
+    if overlap_d:
+        # The discriminator phase needs only the two maps the generator's forward produced and D's own
+        # weights -- nothing of the generator's backward.  It is a string of small, latency-bound
+        # kernels (2^20 rows x <= 128 channels), the generator's backward a string of HBM-bound ones:
+        # issued on a second stream they run side by side (inside a graph capture: a parallel branch).
+        # Every tensor the branch reads stays referenced until the join below (the step's locals and
+        # the step scope's forward cache), so no block is recycled under it; the smoothed labels are
+        # drawn in the reference's order (real, then fake) either way.
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            loss_D_gt, loss_D_nogt = train_D()
+        (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()    # :927-929
+        _start_reduce(optimizer)
+        main.wait_stream(side)
+    else:
+        (args.lambda_seg * l_seg + args.lambda_adv * loss_adv).backward()    # :927-929
+        _start_reduce(optimizer)   # G's gradients are final: their all-reduce runs under the D phase
+        loss_D_gt, loss_D_nogt = train_D()
 
     optimizer.step()
     optimizer_D.step()
     return l_seg.detach(), loss_adv.detach(), (loss_D_gt + loss_D_nogt).detach()
+
+
+_OVERLAP_D = os.environ.get("PCADV_OVERLAP_D", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def pointnet_cls_step(model, cls_loss, optimizer, batch, args):
@@ -515,7 +554,7 @@ class GraphedAdversarialSegStep:
 
     def __init__(self, model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, args, batch_gt,
                  batch_nogt, warmup=3, device_labels=False, fused=False, restore_state=True,
-                 history_pool_gt=None, history_pool_nogt=None, one_pass=None, label_draw=None):
+                 history_pool_gt=None, history_pool_nogt=None, one_pass=None, label_draw=None, overlap_d=None):
         for pool in (history_pool_gt, history_pool_nogt):
             if pool is not None and getattr(pool, "pool_size", 0) > 0:
                 # the pool's swap decisions are host-side ``random`` draws per sample
@@ -549,7 +588,7 @@ class GraphedAdversarialSegStep:
 
         step_fn = adversarial_seg_step_fused if fused else adversarial_seg_step
 
-        extra = {"one_pass": one_pass} if fused else {}
+        extra = {"one_pass": one_pass, "overlap_d": overlap_d} if fused else {}
 
         def run():
             return step_fn(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D,

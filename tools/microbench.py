@@ -152,11 +152,39 @@ def cases(P, N):
     c["conv1_simt"] = (lambda: ops.linear([pts], w3, bias=torch.zeros(64, device=DEV), act=ACT_RELU,
                                           out_dtype=torch.float16, engine=ENGINE_SIMT),
                        P * (12 + 128), 2.0 * P * 3 * 64)
+    s2 = torch.ones(2, device=DEV)
     dy = torch.randn(P, device=DEV)
     val = torch.rand(P, device=DEV)
     idx = torch.randint(0, 128, (P,), device=DEV, dtype=torch.int32)
     c["rowmax_bwd"] = (lambda: ops.rowmax_bwd(dy, val, idx, 128, act=ACT_RELU, out_dtype=torch.float16),
                        P * (12 + 256), 0.0)
+    # fused loss heads over the fp32 logits (utils/trainer.py:899-901, :914)
+    lg50 = torch.randn((P, 50), device=DEV) * 0.3
+    lab = torch.randint(0, 50, (P,), device=DEV)
+    acc2 = torch.zeros(2, device=DEV)
+    pr16, dz16 = torch.empty((P, 64), device=DEV, dtype=torch.float16), torch.empty((P, 64), device=DEV, dtype=torch.float16)
+    c["head_ce"] = (lambda: ops.softmax_head(lg50, ops.HEAD_CE, labels=lab, out_dtype=torch.float16, cols=64,
+                                             dz_gain=256.0, loss_sum=acc2[0:1], valid_count=acc2[1:2],
+                                             probs_out=pr16, dz_out=dz16), P * (200 + 8 + 256), 0.0)
+    c["head_lsm"] = (lambda: ops.softmax_head(lg50, ops.HEAD_LSM, out_dtype=torch.float16, cols=64, probs_out=pr16),
+                     P * (200 + 128), 0.0)
+    dy16 = r16((P, 64))
+    c["lsm_bwd"] = (lambda: ops.logsoftmax_bwd(pr16, dy16, 50, cols=64, out=dz16), P * 384, 0.0)
+    # discriminator: backward of conv4 + ReLU + max over channels (gather kernels)
+    yprev = r16((P, 64)).relu_()
+    wd4 = r16((128, 64), 0.1)
+    dwd = torch.zeros((128, 64), device=DEV)
+    dbd = torch.zeros((128,), device=DEV)
+    c["rowmax_wgrad"] = (lambda: ops.rowmax_wgrad(dy, val, idx, yprev, 128, act=ACT_RELU, dw=dwd, dbias=dbd),
+                         P * (12 + 128), 2.0 * P * 64)
+    c["rowmax_dgrad"] = (lambda: ops.rowmax_dgrad(dy, val, idx, wd4, yprev, act=ACT_RELU, scale=s2[0:1],
+                                                  prev_act=ACT_RELU, out_dtype=torch.float16),
+                         P * (12 + 128 + 128), 2.0 * P * 64)
+    dz64 = r16((P, 64))
+    dw3 = torch.zeros((64, 3), device=DEV)
+    db3 = torch.zeros((64,), device=DEV)
+    c["conv1_wgrad"] = (lambda: ops.wgrad(dz64, [pts], dw=dw3, dbias=db3, scale=s2[1:2], engine=ENGINE_SIMT),
+                        P * (12 + 128), 2.0 * P * 3 * 64)
     dl = torch.randn((P, 50), device=DEV) * 1e-6
     c["amax"] = (lambda: ops.amax_scale(dl), P * 200, 0.0)
     s2 = torch.ones(2, device=DEV)
