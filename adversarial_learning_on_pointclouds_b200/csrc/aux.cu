@@ -228,8 +228,9 @@ using namespace pcadv;
 
 extern "C" long long pcadv_query_workspace(int32_t op, int64_t groups, int64_t rows_per_group, int32_t n) {
   switch (op) {
-    case PCADV_WS_MAXPOOL_BWD_INPLACE:                    // pcadv_maxbwd_args.workspace with dz_inout
-      return groups * (rows_per_group + 3ll * n) * 4ll;
+    case PCADV_WS_MAXPOOL_BWD_INPLACE:                    // pcadv_maxbwd_args.workspace with dz_inout:
+      // per cloud [ends N | list n | dz n | row n | pad to 16 B | n packed 16-byte entries] (misc.cu)
+      return groups * ((rows_per_group + 3ll * n + 3) / 4 * 4 + 4ll * n) * 4ll;
     case PCADV_WS_AMAX_SCALE:                             // pcadv_amax_scale workspace (one uint32)
       return 4;
     default:

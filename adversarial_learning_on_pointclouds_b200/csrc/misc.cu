@@ -160,6 +160,14 @@ __global__ void __launch_bounds__(256) maxbwd_dw_fast_kernel(const pcadv_maxbwd_
   }
 }
 
+// per-cloud workspace of the in-place path, in 32-bit words (see maxbwd_rows_kernel)
+__host__ __device__ __forceinline__ int64_t maxbwd_ws_entry_offset(int64_t N, int64_t n) {
+  return (N + 3 * n + 3) / 4 * 4;
+}
+__host__ __device__ __forceinline__ int64_t maxbwd_ws_ints(int64_t N, int64_t n) {
+  return maxbwd_ws_entry_offset(N, n) + 4 * n;
+}
+
 // dz of the previous layer: one CTA per cloud.  Channels are bucketed by their argmax row
 // in shared memory (count, scan, fill); each warp then sums one touched row in fp32 and
 // adds it once into dz_inout through the previous layer's activation mask.
@@ -206,14 +214,19 @@ __global__ void __launch_bounds__(256) maxbwd_rows_kernel(const pcadv_maxbwd_arg
     }
   }
   __syncthreads();
-  // publish the bucket table: [ends (N) | list (n) | dz (n) | row of list entry (n)] per cloud
-  int* ws = reinterpret_cast<int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
+  // publish the bucket table per cloud: [ends (N) | list (n) | dz (n) | row of list entry (n) | pad |
+  // packed entries (n x int4 {row | -1, channel, dz bits, 0}, 16-byte aligned)]: the 16-bit apply
+  // kernel reads one packed entry per list position instead of three dependent words
+  int* ws = reinterpret_cast<int*>(a.workspace) + static_cast<int64_t>(g) * maxbwd_ws_ints(N, a.n);
   const int cnt = ends[N - 1];
   for (int r = t; r < N; r += 256) ws[r] = ends[r];
+  int4* ent = reinterpret_cast<int4*>(ws + maxbwd_ws_entry_offset(N, a.n));
   for (int c = t; c < a.n; c += 256) {
     ws[N + c] = list[c];
     reinterpret_cast<float*>(ws + N + a.n)[c] = dzv[c];
     ws[N + 2 * a.n + c] = c < cnt ? rowl[c] : -1;
+    const int ch = c < cnt ? list[c] : 0;
+    ent[c] = make_int4(c < cnt ? rowl[c] : -1, ch, c < cnt ? __float_as_int(dzv[ch]) : 0, 0);
   }
 }
 
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply_kernel(const pcadv_maxb
   const int64_t grow = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (grow >= static_cast<int64_t>(a.groups) * N) return;
   const int g = static_cast<int>(grow / N), r = static_cast<int>(grow - static_cast<int64_t>(g) * N);
-  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
+  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * maxbwd_ws_ints(N, a.n);
   const int* ends = ws;
   const int* list = ws + N;
   const float* dzv = reinterpret_cast<const float*>(ws + N + a.n);
@@ -307,7 +320,7 @@ __device__ __forceinline__ void fma8(const uint4 raw, float dz, float (&acc)[8])
   }
 }
 
-template <bool kBf16>
+template <bool kBf16, int KV>
 __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_maxbwd_args a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = static_cast<int>(a.rows_per_group);
@@ -316,16 +329,14 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
   if (wid >= static_cast<int64_t>(a.groups) * segs) return;
   const int g = static_cast<int>(wid / segs);
   const int seg = static_cast<int>(wid - static_cast<int64_t>(g) * segs);
-  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * (N + 3 * a.n);
-  const int* list = ws + N;
-  const float* dzv = reinterpret_cast<const float*>(ws + N + a.n);
-  const int* rowl = ws + N + 2 * a.n;            // -1 beyond the cloud's last entry
+  const int* ws = reinterpret_cast<const int*>(a.workspace) + static_cast<int64_t>(g) * maxbwd_ws_ints(N, a.n);
+  const int4* ent = reinterpret_cast<const int4*>(ws + maxbwd_ws_entry_offset(N, a.n));   // row -1 beyond the last entry
   // one round trip for the segment's rows and its left neighbour: lanes 0..7 the entries, lane 8
   // the entry before the segment; a run starts where the row differs from the entry before it
   const int q0 = seg * kSegEntries;
   int myrow = -1;
-  if (lane < kSegEntries) myrow = q0 + lane < a.n ? rowl[q0 + lane] : -1;
-  else if (lane == kSegEntries) myrow = q0 > 0 ? rowl[q0 - 1] : -2;
+  if (lane < kSegEntries) myrow = q0 + lane < a.n ? __ldg(&ent[q0 + lane].x) : -1;
+  else if (lane == kSegEntries) myrow = q0 > 0 ? __ldg(&ent[q0 - 1].x) : -2;
   const int left = __shfl_sync(0xffffffffu, myrow, lane == 0 ? kSegEntries : (lane - 1) & 31);
   const unsigned valid = __ballot_sync(0xffffffffu, lane < kSegEntries && myrow >= 0);
   const unsigned starts = __ballot_sync(0xffffffffu, lane < kSegEntries && myrow >= 0 && myrow != left);
@@ -337,33 +348,31 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
   const uint4* wbase = reinterpret_cast<const uint4*>(a.w);
   const int64_t ldw4 = a.ldw >> 3;
   while (q < seg_end) {
-    const int row = rowl[q];
-    float acc[kMaxVec][8];
+    const int row = __shfl_sync(0xffffffffu, myrow, q - q0);      // the run starts inside the segment
+    float acc[KV][8];
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j)
+    for (int j = 0; j < KV; ++j)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
     // the touched row of x (mask) and dz: fetched now, used after the run's gathers
     const int64_t grow = static_cast<int64_t>(g) * a.rows_per_group + row;
     const uint4* xrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.x) + grow * a.ldx);
     uint4* drow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.dz_inout) + grow * a.ld_dz);
-    uint4 xr[kMaxVec], dr[kMaxVec];
+    uint4 xr[KV], dr[KV];
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
+    for (int j = 0; j < KV; ++j) {
       const int v = lane + 32 * j;
       if (v < nvec) { xr[j] = xrow[v]; dr[j] = drow[v]; }
     }
     bool more = true;
     while (more) {
-      // metadata of the next 32 list entries, one per lane; the run is a prefix of the window
+      // the next 32 list entries, one packed entry per lane; the run is a prefix of the window
       const int mq = q + lane;
-      int mrow = -1, mc = 0;
-      float mdz = 0.f;
-      if (mq < cnt) {
-        mrow = rowl[mq];
-        if (mrow >= 0) { mc = list[mq]; mdz = dzv[mc]; }
-      }
-      const unsigned same = __ballot_sync(0xffffffffu, mrow == row);
+      int4 m = make_int4(-1, 0, 0, 0);
+      if (mq < cnt) m = __ldg(ent + mq);
+      const int mc = m.y;
+      const float mdz = __int_as_float(m.z);
+      const unsigned same = __ballot_sync(0xffffffffu, m.x == row);
       const int len = same == 0xffffffffu ? 32 : __ffs(~same) - 1;
       more = len == 32;
       for (int i = 0; i < len; i += 4) {               // four gathers in flight
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
           ds[u] = i + u < len ? d : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
+        for (int j = 0; j < KV; ++j) {
           const int v = lane + 32 * j;
           if (v < nvec) {
             uint4 rw[4];
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
     }
     // one read-modify-write of the touched row, through the previous layer's activation mask
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
+    for (int j = 0; j < KV; ++j) {
       const int v = lane + 32 * j;
       if (v < nvec) {
         const uint32_t x4[4] = {xr[j].x, xr[j].y, xr[j].z, xr[j].w};
@@ -418,6 +427,15 @@ __global__ void __launch_bounds__(256) maxbwd_rows_apply16_kernel(const pcadv_ma
   }
 }
 
+template <bool kBf16>
+void launch_apply16(const pcadv_maxbwd_args& a, unsigned blocks, cudaStream_t s) {
+  const int kv = (a.k / 8 + 31) / 32;             // 16-byte vectors per lane
+  if (kv <= 1) maxbwd_rows_apply16_kernel<kBf16, 1><<<blocks, 256, 0, s>>>(a);
+  else if (kv == 2) maxbwd_rows_apply16_kernel<kBf16, 2><<<blocks, 256, 0, s>>>(a);
+  else if (kv == 3) maxbwd_rows_apply16_kernel<kBf16, 3><<<blocks, 256, 0, s>>>(a);
+  else maxbwd_rows_apply16_kernel<kBf16, 4><<<blocks, 256, 0, s>>>(a);
+}
+
 // dW / dbias, 16-bit x rows gathered with 16-byte loads: one CTA per channel c, 8 warps stride
 // over the clouds (four clouds per trip), no atomics.
 template <bool kBf16>
@@ -434,21 +452,30 @@ __global__ void __launch_bounds__(256) maxbwd_dw16_kernel(const pcadv_maxbwd_arg
   float bsum = 0.f;
   const uint4* xbase = reinterpret_cast<const uint4*>(a.x);
   const int64_t ldx4 = a.ldx >> 3;
+  // the (dz, argmax row) of a trip's four clouds are fetched one trip ahead, so that the row gathers
+  // of this trip and the metadata of the next are in flight together
+  float ndz[4];
+  int64_t nr[4];
+  auto fetch = [&](int g0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + 8 * u;
+      ndz[u] = 0.f;
+      nr[u] = 0;
+      if (g < a.groups) {
+        const int64_t gc = static_cast<int64_t>(g) * a.n + c;
+        ndz[u] = __ldg(a.dg + gc) * act_grad_from_output(__ldg(a.gval + gc), a.act, a.slope);
+        nr[u] = static_cast<int64_t>(g) * a.rows_per_group + __ldg(a.idx + gc);
+      }
+    }
+  };
+  fetch(warp);
   for (int g0 = warp; g0 < a.groups; g0 += 32) {
     float dz[4];
     int64_t r[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int g = g0 + 8 * u;
-      dz[u] = 0.f;
-      r[u] = 0;
-      if (g < a.groups) {
-        const int64_t gc = static_cast<int64_t>(g) * a.n + c;
-        dz[u] = a.dg[gc] * act_grad_from_output(a.gval[gc], a.act, a.slope);
-        r[u] = static_cast<int64_t>(g) * a.rows_per_group + a.idx[gc];
-      }
-      bsum += dz[u];
-    }
+    for (int u = 0; u < 4; ++u) { dz[u] = ndz[u]; r[u] = nr[u]; bsum += dz[u]; }
+    if (g0 + 32 < a.groups) fetch(g0 + 32);
     if (a.dw) {
 #pragma unroll
       for (int j = 0; j < kMaxVec; ++j) {
@@ -878,8 +905,8 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
     if (all16) {
       const int64_t items = static_cast<int64_t>(a->groups) * ((a->n + kSegEntries - 1) / kSegEntries);
       const unsigned blocks = static_cast<unsigned>((items + 7) / 8);
-      if (a->x_dtype == PCADV_BF16) maxbwd_rows_apply16_kernel<true><<<blocks, 256, 0, s>>>(*a);
-      else maxbwd_rows_apply16_kernel<false><<<blocks, 256, 0, s>>>(*a);
+      if (a->x_dtype == PCADV_BF16) launch_apply16<true>(*a, blocks, s);
+      else launch_apply16<false>(*a, blocks, s);
     } else {
       const int64_t total_rows = static_cast<int64_t>(a->groups) * a->rows_per_group;
       maxbwd_rows_apply_kernel<<<static_cast<unsigned>((total_rows + 7) / 8), 256, 0, s>>>(*a);

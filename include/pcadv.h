@@ -209,7 +209,7 @@ typedef struct pcadv_maxbwd_args {
   int32_t dz_dtype;
   void* dz_inout;             /* [rows, k] or NULL */
   int64_t ld_dz;
-  void* workspace;            /* with dz_inout: >= groups * (rows_per_group + 3 * n) * 4 bytes */
+  void* workspace;            /* with dz_inout: pcadv_query_workspace(PCADV_WS_MAXPOOL_BWD_INPLACE, ...) bytes, 16-byte aligned */
   int64_t rows_per_group;
   const float* dg;            /* [groups, n] */
   const float* gval;          /* [groups, n] pooled post-activation value */

@@ -97,7 +97,8 @@ def test_batchnorm_rows_matches_torch(rows, C, dtype, relu):
 def test_query_workspace_matches_the_documented_sizes():
     from adversarial_learning_on_pointclouds_b200 import ops, _lib
     assert ops.query_workspace(_lib.WS_MAXPOOL_BWD_INPLACE, groups=256, rows_per_group=4096, n=2048) == \
-        256 * (4096 + 3 * 2048) * 4
+        256 * (4096 + 3 * 2048 + 4 * 2048) * 4
+    assert ops.query_workspace(_lib.WS_MAXPOOL_BWD_INPLACE, groups=3, rows_per_group=201, n=1024) % 16 == 0
     assert ops.query_workspace(_lib.WS_AMAX_SCALE) == 4
     with pytest.raises(_lib.PcadvError):
         ops.query_workspace(99)
