@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) group_colsum16_kernel(const uint16_t* __r
 // contiguous, fully coalesced output row.
 // =====================================================================================
 template <int K>
-__global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_args a) {
+__global__ void __launch_bounds__(256, 4) first_layer_kernel(const pcadv_linear_args a) {
   const int groups = a.n >> 3;                       // threads per point
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int cg = static_cast<int>(tid % groups) * 8;
@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_arg
   const float* x = reinterpret_cast<const float*>(a.seg[0].ptr);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x / groups;
   const int gidx = static_cast<int>(tid % groups);
+  const bool relu16 = a.act == PCADV_ACT_RELU && a.out_dtype != PCADV_F32;
   // two points per trip: both xyz loads are in flight before either is used.  The trip count is
   // warp-uniform (bounded by the warp's first point) because the sign-bit words are combined
   // with full-warp shuffles.
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_arg
         float acc = b[i];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc = fmaf(xv[u][k], w[i][k], acc);
-        v[i] = apply_act(acc, a.act, a.slope);
+        v[i] = relu16 ? acc : apply_act(acc, a.act, a.slope);   // 16-bit ReLU: applied on the packed halves below
       }
       if (a.out_dtype == PCADV_F32) {
         if (r_ok) {
@@ -417,6 +418,11 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const pcadv_linear_arg
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           pk[i] = a.out_dtype == PCADV_F16 ? pack_f16x2_sat(v[2 * i], v[2 * i + 1]) : pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (relu16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            pk[i] = a.out_dtype == PCADV_F16 ? relu_packed<false>(pk[i]) : relu_packed<true>(pk[i]);
+        }
         if (r_ok)
           *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + r * a.ld_out + cg) =
               make_uint4(pk[0], pk[1], pk[2], pk[3]);
