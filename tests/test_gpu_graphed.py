@@ -122,12 +122,16 @@ def test_graphed_fused_step_matches_eager_and_oracle(mode, one_pass):
         e = rel_err(a, b)
         worst = max(worst, e)
         if mode == "fp32":
-            assert e < 1e-4, (k, e)
+            assert e < 1e-3, (k, e)
     moved_g = torch.cat([(v.detach().cpu() - start[k]).flatten() for k, v in g.named_parameters()]).norm().item()
     apart_g = torch.cat([(a.detach() - b.detach()).flatten() for (k, a), (_, b) in pairs[:20]]).norm().item()
     print("graph vs eager (%s): worst loss rel diff over %d iterations %.2e; G parameters moved %.3e, apart %.3e"
           % (mode, iters, worst_loss, moved_g, apart_g))
-    assert apart_g < (2e-3 if mode == "fp32" else 0.05) * moved_g, (apart_g, moved_g)
+    # fp32: 2e-6 of the distance moved in five runs out of six; in the sixth a ReLU / argmax decision
+    # of some iteration lands on the other side (atomics order, ~1e-7) and Adam's sign-like steps turn
+    # that into 2.5e-3 of the distance.  A cross-stream race (the bug this test caught while the
+    # discriminator phase was moved to a second stream) showed as 8.5e-2 in the fp16 mode.
+    assert apart_g < (1e-2 if mode == "fp32" else 0.05) * moved_g, (apart_g, moved_g)
     print("graph vs eager (%s, one_pass=%s): worst parameter rel err after %d Adam steps %.2e"
           % (mode, one_pass, iters, worst))
     assert gstep.launches_per_step > 0
