@@ -306,7 +306,11 @@ class _Harness:
             self.barrier()
             total = sum(a.elapsed_time(b) for a, b in evs)
         ms = torch.tensor([total], device=self.dev)
+        self.last_by_rank = [total]
         if self.world > 1:
+            every = [torch.zeros_like(ms) for _ in range(self.world)]
+            self.dist.all_gather(every, ms)
+            self.last_by_rank = [float(t.item()) for t in every]
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return ms.item()
 
@@ -454,7 +458,7 @@ def run_cuda_adv(args):
         g.precision = d.precision = precision
         opt = torch.optim.Adam(g.parameters(), lr=1e-4, betas=(0.9, 0.999), fused=True, capturable=capturable)
         optD = torch.optim.Adam(d.parameters(), lr=1e-5, betas=(0.9, 0.999), fused=True, capturable=capturable)
-        if world > 1 and distributed:
+        if world > 1 and distributed and not os.environ.get("PCADV_BENCH_NO_EXCHANGE"):
             opt, optD = DistributedOptimizer(opt), DistributedOptimizer(optD)
         return g, d, opt, optD
 
@@ -530,6 +534,7 @@ def run_cuda_adv(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms = H.timed(resident_step, args.steps, flush=flush)
+    ms_by_rank = [v / args.steps for v in H.last_by_rank]
     for _ in range(2):
         e2e_step()
     ms_e2e = H.timed(e2e_step, args.steps, flush=flush)
@@ -595,6 +600,11 @@ def run_cuda_adv(args):
                      "trainer.adversarial_seg_step_fused)" if fused else
                      "reference-shaped modules + torch losses (trainer.adversarial_seg_step)"),
         "clocks": sampler.summary(),
+        "ms_per_step_by_rank": [round(v, 3) for v in ms_by_rank],
+        "gradient_exchange": ("none (PCADV_BENCH_NO_EXCHANGE: independent replicas, diagnostic)"
+                              if os.environ.get("PCADV_BENCH_NO_EXCHANGE") else
+                              ("NCCL all-reduce (AVG) of the gradient slabs in place, inside the graph; G's under the "
+                               "discriminator phase" if world > 1 else "single GPU")),
         "roofline": roofline,
         "graph_check": graph_check,
         "kernel_rooflines": kernel_rooflines(ksum, None, peaks, args.steps),
