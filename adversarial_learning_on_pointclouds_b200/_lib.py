@@ -114,6 +114,8 @@ SYMBOLS = {
     "pcadv_logsoftmax_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
                                        C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_void_p]),
+    "pcadv_lse_ratio": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int64, C.c_void_p]),
     "pcadv_round_residual": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "pcadv_bmm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,

@@ -350,10 +350,42 @@ __global__ void __launch_bounds__(256) round_residual_kernel(const float* __rest
   if (sub == 0 && c < cols) atomicAdd(out + c, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
 }
 
+
+// StackDiscNet's custom activation (models/discriminator.py:153-159): per row of the shape logits
+// [rows, S], z = logsumexp_c x[r, c], y[r] = z / (z + 1); backward dx[r, c] = dy[r] * softmax(x[r, :])[c]
+// / (z + 1)^2.  One thread per row (S <= 64): rows are short and contiguous.
+__global__ void __launch_bounds__(256) lse_ratio_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int S,
+                                                        const float* __restrict__ dy, float* __restrict__ y,
+                                                        float* __restrict__ dx, int64_t ld_dx) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* xr = x + r * ld;
+  float m = xr[0];
+  for (int c = 1; c < S; ++c) m = fmaxf(m, xr[c]);
+  float s = 0.f;
+  for (int c = 0; c < S; ++c) s += expf(xr[c] - m);
+  const float z = m + logf(s);
+  if (y) y[r] = z / (z + 1.f);
+  if (dx) {
+    const float g = dy[r] / ((z + 1.f) * (z + 1.f) * s);
+    for (int c = 0; c < S; ++c) dx[r * ld_dx + c] = g * expf(xr[c] - m);
+  }
+}
+
 }  // namespace
 }  // namespace pcadv
 
 using namespace pcadv;
+
+extern "C" int pcadv_lse_ratio(const float* x, int64_t ld, int64_t rows, int32_t S, const float* dy, float* y,
+                               float* dx, int64_t ld_dx, void* stream) {
+  PCADV_CHECK_ARG(x && rows >= 0 && S > 0 && S <= 64 && (y || (dx && dy)), "pcadv_lse_ratio: bad args (S <= 64)");
+  if (rows == 0) return 0;
+  lse_ratio_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ld, rows, S, dy, y, dx, ld_dx);
+  PCADV_LAUNCHED();
+  return 0;
+}
 
 extern "C" int pcadv_round_residual(const float* src, int64_t ld, int64_t rows, int32_t cols, const float* scale,
                                     int32_t dtype, float* out, void* stream) {

@@ -375,5 +375,43 @@ class RegularizerFunction(torch.autograd.Function):
         return ops.ortho_reg_bwd(diff, t, norms, dloss.contiguous().float())
 
 
+class LogSoftmaxRowsFunction(torch.autograd.Function):
+    """log_softmax over the columns of point-major logits [rows, n] (fp32), forward and backward on
+    the loss-head kernels (``pcadv_softmax_head`` / ``pcadv_logsoftmax_bwd``): the
+    ``F.log_softmax(x.view(-1, k), dim=-1)`` of PointNetDenseCls (models/pointnet.py:341)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        if x.stride(1) != 1 or x.dtype != torch.float32:
+            x = x.contiguous().float()
+        lp, _ = ops.softmax_head(x, ops.HEAD_LSM, out_dtype=torch.float32)
+        ctx.save_for_backward(lp)
+        return lp
+
+    @staticmethod
+    def backward(ctx, dy):
+        (lp,) = ctx.saved_tensors
+        if dy.stride(1) != 1 or dy.dtype != torch.float32:
+            dy = dy.contiguous().float()
+        return ops.logsoftmax_bwd(lp, dy, lp.shape[1])
+
+
+class LseRatioFunction(torch.autograd.Function):
+    """StackDiscNet.custom_activation on point-major shape logits [rows, S]: z / (z + 1) with
+    z = logsumexp over S (models/discriminator.py:153-159), one kernel each way (``pcadv_lse_ratio``)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        if x.stride(1) != 1 or x.dtype != torch.float32:
+            x = x.contiguous().float()
+        ctx.save_for_backward(x)
+        return ops.lse_ratio(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.lse_ratio(x, dy.contiguous().float())
+
+
 __all__ = ["MLPSpec", "PointMLPFunction", "point_mlp", "BmmFunction", "RegularizerFunction",
-           "ACT_NONE"]
+           "LogSoftmaxRowsFunction", "LseRatioFunction", "ACT_NONE"]

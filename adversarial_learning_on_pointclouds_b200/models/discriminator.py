@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import ACT_LEAKY, ACT_NONE, ACT_RELU
-from ._mlp import point_mlp
+from ._mlp import point_mlp, LseRatioFunction
 
 _RELU = (ACT_RELU, 0.0)
 _NONE = (ACT_NONE, 0.0)
@@ -171,4 +171,5 @@ class StackDiscNet(nn.Module):
                       reduce="channels", box=box)                                 # [B*N]
         s = point_mlp(prec, m.view(B * N, 1), [self.conv5], [_NONE])              # [B*N, S]
         shape_logits = s.view(B, N, s.shape[-1]).transpose(1, 2)                           # B x S x N
-        return shape_logits, self.custom_activation(shape_logits)
+        # custom_activation on the point-major rows (the same numbers as the B x S x N form above)
+        return shape_logits, LseRatioFunction.apply(s).view(B, N, 1)

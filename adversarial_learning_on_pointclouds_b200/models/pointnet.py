@@ -16,7 +16,7 @@ import torch.nn as nn
 from .. import ops
 from ..ops import ACT_NONE, ACT_RELU
 from ._seg import SegFunction, PARAM_NAMES as _SEG_PARAMS
-from ._mlp import point_mlp, BmmFunction, RegularizerFunction
+from ._mlp import point_mlp, BmmFunction, RegularizerFunction, LogSoftmaxRowsFunction
 
 _RELU = (ACT_RELU, 0.0)
 _NONE = (ACT_NONE, 0.0)
@@ -277,7 +277,7 @@ class PointNetDenseCls(nn.Module):
         h = point_mlp(prec, pointfeat.reshape(B * N, 64),
                       [(w1[:, 1024:], None), self.conv2, self.conv3, self.conv4],
                       [_RELU, _RELU, _RELU, _NONE], group=N, group_bias=cb)       # P x k
-        h = torch.nn.functional.log_softmax(h.view(-1, self.num_classes), dim=-1)
+        h = LogSoftmaxRowsFunction.apply(h.view(-1, self.num_classes))             # :341
         return h.view(B, N, self.num_classes), trans_feat
 
 

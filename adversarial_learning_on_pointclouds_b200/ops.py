@@ -556,6 +556,25 @@ def logsoftmax_bwd(lp, dy, n, *, scale=None, out_dtype=torch.float32, cols=None,
     return dz
 
 
+def lse_ratio(x, dy=None):
+    """StackDiscNet's z / (z + 1), z = logsumexp over the columns of x [rows, S] (fp32): see
+    ``pcadv_lse_ratio``.  Without ``dy``: returns y [rows]; with ``dy`` [rows]: returns dx [rows, S]."""
+    p, ld, dt = _mat(x)
+    if dt != F32:
+        raise ValueError("lse_ratio expects fp32")
+    rows, S = x.shape
+    if dy is None:
+        y = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        if rows:
+            _call("lse_ratio", _lib.lib().pcadv_lse_ratio, p, ld, rows, S, None, _ptr(y), None, 0, _stream(), rows=rows)
+        return y
+    dx = torch.empty((rows, S), dtype=torch.float32, device=x.device)
+    if rows:
+        _call("lse_ratio_bwd", _lib.lib().pcadv_lse_ratio, p, ld, rows, S, _f32(dy, rows), None, _ptr(dx), S, _stream(),
+              rows=rows)
+    return dx
+
+
 def round_residual(src, scale, out_dtype):
     """Column sums of what converting ``src * scale`` (fp32 [rows, cols <= 64]) to ``out_dtype`` drops:
     see ``pcadv_round_residual``.  Returns fp32 [cols]."""

@@ -594,8 +594,17 @@ class GraphedAdversarialSegStep:
             return step_fn(model, model_D, gan_loss, seg_loss, optimizer, optimizer_D,
                            self.static_gt, self.static_nogt, args, label_fn=label_fn, **extra)
 
+        # The smoothed labels travel like the batch: drawn on the host, copied to device staging on a
+        # copy stream while the previous iteration computes, moved into the graph's static buffers
+        # with a device-to-device copy at the start of the step (no host -> device copy on the
+        # critical path, none queued behind the next batch's copy on the DMA engine).
+        if not device_labels:
+            self.stage_real, self.stage_fake = torch.empty_like(self.label_real), torch.empty_like(self.label_fake)
+            self._label_stream = torch.cuda.Stream()
+        self._labels_staged = self._labels_consumed = None
         self._draw_labels(0)
-        self._upload_labels()
+        self._stage_labels()
+        self._consume_labels()
         # The warm-up iterations (allocator / lazy optimizer state before capture) are real optimizer
         # steps; they must not count as training: parameters, optimizer state and the device
         # generator are put back afterwards, in place, so the first replay is iteration 1 of the
@@ -674,15 +683,31 @@ class GraphedAdversarialSegStep:
         self.host_real[slot].uniform_(0.7, 1.05)
         self.host_fake[slot].uniform_(0.0, 0.305)
 
-    def _upload_labels(self):
+    def _stage_labels(self):
+        """Host slot -> device staging, on the label copy stream."""
         if self.device_labels:
             return
-        slot = self._slot
-        self.label_real.copy_(self.host_real[slot], non_blocking=True)
-        self.label_fake.copy_(self.host_fake[slot], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        slot, ls = self._slot, self._label_stream
+        if self._labels_consumed is not None:
+            ls.wait_event(self._labels_consumed)           # the previous labels left the staging buffers
+        with torch.cuda.stream(ls):
+            self.stage_real.copy_(self.host_real[slot], non_blocking=True)
+            self.stage_fake.copy_(self.host_fake[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(ls)
         self._copied[slot] = ev
+        self._labels_staged = ev
+
+    def _consume_labels(self):
+        """Device staging -> the graph's static label buffers, on the current stream."""
+        if self.device_labels:
+            return
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._labels_staged)
+        self.label_real.copy_(self.stage_real, non_blocking=True)
+        self.label_fake.copy_(self.stage_fake, non_blocking=True)
+        self._labels_consumed = torch.cuda.Event()
+        self._labels_consumed.record(cur)
 
     def __call__(self, batch_gt=None, batch_nogt=None):
         """Copy the batch into the static buffers (skipped when None: reuse), draw labels, replay.
@@ -693,10 +718,11 @@ class GraphedAdversarialSegStep:
         if batch_nogt is not None:
             for dst, src in zip(self.static_nogt, batch_nogt):
                 dst.copy_(src, non_blocking=True)
-        self._upload_labels()
+        self._consume_labels()
         self.graph.replay()
         self._slot ^= 1
         self._draw_labels(self._slot)                  # next iteration's labels, under the GPU's shadow
+        self._stage_labels()
         return self.losses
 
 

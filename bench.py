@@ -510,14 +510,26 @@ def run_cuda_adv(args):
 
         gstep.prefetch(host_gt, host_nogt)
 
+        loss_slots = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+        e2e_state = {"i": 0}
+
         def e2e_step():
             # this step's batch was put on the wire (pinned host -> device staging, copy stream)
             # while the previous step computed; the next batch's copy starts right after this
-            # step is launched, so every timed step still carries one full host -> device copy
+            # step is launched, so every timed step still carries one full host -> device copy.
+            # Every step's three losses are read back to pinned host memory; the host waits for the
+            # PREVIOUS step's read while this step runs (a training loop that logs with a lag of one
+            # iteration), so the graph launch of step i + 1 is not serialised behind step i.
+            i = e2e_state["i"]
             losses = gstep.step_prefetched()
             gstep.prefetch(host_gt, host_nogt)
-            loss_host.copy_(losses, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            loss_slots[i & 1].copy_(losses, non_blocking=True)
+            loss_events[i & 1].record()
+            if i > 0:
+                loss_events[(i - 1) & 1].synchronize()
+                loss_host.copy_(loss_slots[(i - 1) & 1])
+            e2e_state["i"] = i + 1
     else:
         def resident_step():
             step(dev_gt, dev_nogt)

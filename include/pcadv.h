@@ -315,6 +315,12 @@ int pcadv_logsoftmax_bwd(const void* lp, int32_t lp_dtype, int64_t ld_lp, const 
                          int32_t dy_dtype, int64_t ld_dy, int64_t rows, int32_t n, const float* scale,
                          void* dz, int32_t dz_dtype, int64_t ld_dz, int32_t dz_cols, void* stream);
 
+/* StackDiscNet.custom_activation (models/discriminator.py:153-159) over point-major shape logits
+ * x [rows, S] (fp32, S <= 64): z = logsumexp_c x[r, c];  y[r] = z / (z + 1)  (y nullable);
+ * with dy and dx given: dx[r, c] = dy[r] * softmax(x[r, :])[c] / (z + 1)^2. */
+int pcadv_lse_ratio(const float* x, int64_t ld, int64_t rows, int32_t S, const float* dy, float* y, float* dx,
+                    int64_t ld_dx, void* stream);
+
 /* out[c] += sum_r (v - round_dtype(v)), v = src[r, c] * (*scale): the column sums of what the 16-bit
  * conversion of a gradient matrix drops (dtype = PCADV_F16 | PCADV_BF16, cols <= 64; the caller
  * zero-fills out).  Added to a bias gradient formed from the 16-bit dz it restores the exact fp32
