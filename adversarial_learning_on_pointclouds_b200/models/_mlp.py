@@ -39,8 +39,11 @@ class MLPSpec:
     folded tiled-global-feature columns of models/pointnet.py:135-136).
     """
 
-    def __init__(self, acts, reduce=None, group=0, tap=None, box=None):
+    def __init__(self, acts, reduce=None, group=0, tap=None, box=None, extra_segs=0):
         self.acts, self.reduce, self.group, self.tap = list(acts), reduce, int(group), tap
+        # the first layer reads the K-concat [x | extra segments] (models/pointnet.py:246-251 without
+        # building the concatenated map): the extra [rows, k_i] fp32 tensors follow the parameters
+        self.extra_segs = int(extra_segs)
         # GradBox of a packed 16-bit input (models/_seg.py): the input gradient is then returned
         # in the input's dtype, still carrying this backward's power-of-two scale, which is left
         # in the box for the producer of the input
@@ -58,7 +61,13 @@ class PointMLPFunction(torch.autograd.Function):
         if not x.is_cuda:
             raise RuntimeError("libpcadv layers need CUDA tensors; there is no CPU path")
         nl = len(spec.acts)
+        extra = list(params[2 * nl:])
+        params = params[:2 * nl]
+        if len(extra) != spec.extra_segs:
+            raise ValueError("PointMLPFunction: spec.extra_segs does not match the arguments")
         layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
+        if extra:
+            return PointMLPFunction._forward_segments(ctx, prec, spec, [x] + extra, gb, layers, params)
         # Inside a step scope (``weight_cache``) a forward over the very same input and weights is
         # not repeated: the trainer evaluates D(log_softmax(pred_nogt)) in the G phase and again on
         # the detached tensor in the D phase (utils/trainer.py:916, :951-953).
@@ -162,8 +171,40 @@ class PointMLPFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _forward_segments(ctx, prec, spec, xs, gb, layers, params):
+        """Forward with a multi-segment first layer: every segment is a [rows, k_i] fp32 matrix
+        (k_i a multiple of 64 in the 16-bit modes); no reduction, no tap."""
+        if spec.reduce is not None or spec.tap is not None:
+            raise ValueError("a multi-segment input supports plain chains only")
+        segs = []
+        for x in xs:
+            if x.dim() != 2:
+                raise ValueError("input segments must be [rows, k] matrices")
+            if x.dtype != torch.float32 or x.stride(1) != 1:
+                x = x.contiguous().float()
+            if prec.scaled and x.shape[0] >= 128:
+                x = ops.convert(x, prec.act_dtype, cols_pad=(x.shape[1] + 63) // 64 * 64)
+            segs.append(x)
+        if gb is not None:
+            gb = gb.contiguous().float()
+        ybits = []
+        ys = chain_forward(prec, segs, layers, final_fp32=True, rows_per_group=spec.group if gb is not None else 0,
+                           group_bias=gb, bits=ybits)
+        ctx.prec, ctx.spec = prec, spec
+        ctx.bcn, ctx.packed_in = None, False
+        ctx.n_x, ctx.n_ys = len(segs), len(ys)
+        ctx.seg_widths = [x.shape[1] for x in xs]
+        ctx.has_red, ctx.has_gb = False, gb is not None
+        ctx.bit_slots = [i for i, t in enumerate(ybits) if t is not None]
+        ctx.save_for_backward(*(segs + ys + list(params) + [ybits[i] for i in ctx.bit_slots]))
+        _tape(spec, segs[0], ys, None, None, ys[-1], False)
+        return ys[-1]
+
+    @staticmethod
     def backward(ctx, d_out, d_tap=None):
         prec, spec = ctx.prec, ctx.spec
+        if spec.extra_segs:
+            return PointMLPFunction._backward_segments(ctx, d_out)
         sv = list(ctx.saved_tensors)
         nb = len(ctx.bit_slots)
         ybits = [None] * ctx.n_ys
@@ -321,12 +362,73 @@ class PointMLPFunction(torch.autograd.Function):
         return (None, None, dx, dgb, *flat)
 
 
+    @staticmethod
+    def _backward_segments(ctx, d_out):
+        prec, spec = ctx.prec, ctx.spec
+        sv = list(ctx.saved_tensors)
+        nb = len(ctx.bit_slots)
+        ybits = [None] * ctx.n_ys
+        for slot, t in zip(ctx.bit_slots, sv[len(sv) - nb:]):
+            ybits[slot] = t
+        sv = sv[:len(sv) - nb]
+        segs, ys = sv[:ctx.n_x], sv[ctx.n_x:ctx.n_x + ctx.n_ys]
+        params = sv[ctx.n_x + ctx.n_ys:]
+        nl = len(spec.acts)
+        layers = [Layer(params[2 * i], params[2 * i + 1], *spec.acts[i]) for i in range(nl)]
+        need = ctx.needs_input_grad[4:4 + 2 * nl]
+        need_w = [need[2 * i] for i in range(nl)]
+        need_b = [need[2 * i + 1] for i in range(nl)]
+        need_x = ctx.needs_input_grad[2] or any(ctx.needs_input_grad[4 + 2 * nl:])
+        n_out = 4 + 2 * nl + spec.extra_segs
+        if d_out is None:
+            return (None,) * n_out
+        d_out = d_out.contiguous().float()
+        scale2 = ops.amax_scale(d_out) if prec.scaled else None
+        S = scale2[0:1] if prec.scaled else None
+        inv = scale2[1:2] if prec.scaled else None
+        pool = None
+        if any(need_w) or any(need_b):
+            pad = lambda n: (n + 63) // 64 * 64
+            pool = ZeroPool(ZeroPool.size_for([(pad(L.w.shape[0]), pad(L.w.shape[1])) for L in layers]), d_out.device)
+        L = layers[-1]
+        dz_last = prepare_dz(prec, d_out, scale2, mask=ys[-1], mask_act=L.act, mask_slope=L.slope)
+        db_residual = None
+        if prec.scaled and L.act == ACT_NONE and need_b[-1] and d_out.shape[1] <= 64:
+            db_residual = ops.round_residual(d_out, S, prec.act_dtype)
+        grads, dx, dz0 = chain_backward(prec, dz_last, list(segs), ys, layers, need_w, need_b, need_x, scale2,
+                                        bits=ybits, pool=pool)
+        if db_residual is not None and grads[-1] is not None and grads[-1][1] is not None:
+            grads[-1][1].add_(db_residual[:grads[-1][1].shape[0]] * inv)
+        dgb = None
+        if ctx.has_gb and ctx.needs_input_grad[3]:
+            rows, n0 = dz0.shape[0], layers[0].w.shape[0]
+            dgb = torch.zeros((rows // spec.group, dz0.shape[1]), dtype=torch.float32, device=d_out.device)
+            ops.wgrad(dz0, [], dgroup_bias=dgb, rows_per_group=spec.group)
+            dgb = dgb[:, :n0] * inv if prec.scaled else dgb[:, :n0]
+        flat = []
+        for i in range(nl):
+            dw, db = grads[i] if grads[i] is not None else (None, None)
+            flat.append(dw.reshape(params[2 * i].shape) if dw is not None else None)
+            flat.append(db)
+        dxs, off = [], 0
+        for w_ in ctx.seg_widths:                       # the K-concat's gradient, segment by segment (views)
+            dxs.append(dx[:, off:off + w_] if dx is not None else None)
+            off += w_
+        return (None, None, dxs[0], dgb, *flat, *dxs[1:])
+
+
 def point_mlp(prec, x, layers, acts, reduce=None, group=0, tap=None, group_bias=None, box=None):
     """Convenience wrapper: ``layers`` are nn.Conv1d / nn.Linear modules or
-    (weight, bias | None) pairs."""
+    (weight, bias | None) pairs.  ``x`` may be a list of [rows, k_i] matrices: the first layer then
+    reads their K-concat without it being built."""
     params = []
     for m in layers:
         params += [m.weight, m.bias] if hasattr(m, "weight") else [m[0], m[1]]
+    if isinstance(x, (list, tuple)):
+        if len(x) > 1:
+            return PointMLPFunction.apply(prec, MLPSpec(acts, reduce, group, tap, box, extra_segs=len(x) - 1), x[0],
+                                          group_bias, *params, *x[1:])
+        x = x[0]
     return PointMLPFunction.apply(prec, MLPSpec(acts, reduce, group, tap, box), x, group_bias, *params)
 
 

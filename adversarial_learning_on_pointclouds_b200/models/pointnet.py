@@ -227,8 +227,9 @@ class PointNetSeg_regulization(nn.Module):
         self.fc4 = torch.nn.Linear(128, self.output_dim)
 
     def forward(self, x, cls):                  # B x N x 3, B x 1 x 16
-        # Composition of the generic Functions (fp32 tensors between them); the fused
-        # single-Function path is PointNetSeg's -- this variant is not on the benchmarked path.
+        # Composition of the generic Functions (fp32 tensors between them, the T-Net transforms sit
+        # between the trunk layers); the fused single-Function path is PointNetSeg's -- this variant
+        # is not on the benchmarked path.
         B, N, _ = x.shape
         P = B * N
         prec = _prec(self)
@@ -246,7 +247,8 @@ class PointNetSeg_regulization(nn.Module):
         w1 = self.fc1.weight
         cb = point_mlp(prec, torch.cat([g, cls.reshape(B, -1).float()], 1),
                        [(w1[:, 960:], self.fc1.bias)], [_NONE])          # B x 256
-        logits = point_mlp(prec, torch.cat([x1, x2, x3, x4, x5], 1),
+        # x1..x5 go in as five K-segments: the 960-channel map is not built either
+        logits = point_mlp(prec, [x1, x2, x3, x4, x5],
                            [(w1[:, :960], None), self.fc2, self.fc3, self.fc4],
                            [_RELU, _RELU, _RELU, _NONE], group=N, group_bias=cb)   # P x k
         return logits.view(B, N, logits.shape[-1]).transpose(1, 2), g.unsqueeze(2), trans_feat
