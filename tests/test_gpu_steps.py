@@ -53,9 +53,9 @@ def _check(tag, mode, mods_params_start, golden=None):
     for name, mod, params, start in mods_params_start:
         apart, moved = _distance(mod, params, start)
         print("%s %s %s: parameters moved %.3e, CUDA path apart from the oracle %.3e" % (tag, mode, name, moved, apart))
-        # fp32: summation order only (a flipped decision under Adam costs ~1e-3 of the distance moved);
+        # fp32: summation order only, measured 1e-5 (one flipped decision under Adam: ~2.5e-3 of the distance moved);
         # fp16: the rounding of the mode under the sign-like first steps of Adam on 512-point batches (measured 0.14-0.17)
-        assert apart <= (2e-3 if mode == "fp32" else 0.3) * moved + 1e-7, (name, apart, moved)
+        assert apart <= (1e-2 if mode == "fp32" else 0.3) * moved + 1e-7, (name, apart, moved)
         if golden is not None and mode == "fp32":
             for k, v in mod.state_dict().items():
                 # biases start at zero and are lr-sized after a few steps (1e-5 .. 1e-4), so one decision
