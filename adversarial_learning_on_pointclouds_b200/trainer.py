@@ -276,7 +276,7 @@ class GraphedStep:
         from . import _lib
         before = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = run()
         self.launches_per_step = _lib.launch_count() - before
 
@@ -548,13 +548,15 @@ class GraphedAdversarialSegStep:
     The constructor runs ``warmup`` iterations on the first batch before capturing (allocator
     warm-up, lazy optimizer state).  With ``restore_state`` (default) the parameters, the optimizer
     state and the device generator are restored in place afterwards, so constructing the object
-    does not advance training; the CPU generator is only consumed by the label draws of the real
-    iterations, in the reference's order.
+    does not advance training.  The smoothed labels are drawn by a worker thread from a private generator
+    cloned from torch's CPU generator at construction (the reference's sequence of draws; the global
+    generator itself is left alone); ``close()`` joins the worker.
     """
 
     def __init__(self, model, model_D, gan_loss, seg_loss, optimizer, optimizer_D, args, batch_gt,
                  batch_nogt, warmup=3, device_labels=False, fused=False, restore_state=True,
-                 history_pool_gt=None, history_pool_nogt=None, one_pass=None, label_draw=None, overlap_d=None):
+                 history_pool_gt=None, history_pool_nogt=None, one_pass=None, label_draw=None, overlap_d=None,
+                 threaded_labels=True):
         for pool in (history_pool_gt, history_pool_nogt):
             if pool is not None and getattr(pool, "pool_size", 0) > 0:
                 # the pool's swap decisions are host-side ``random`` draws per sample
@@ -602,6 +604,14 @@ class GraphedAdversarialSegStep:
             self.stage_real, self.stage_fake = torch.empty_like(self.label_real), torch.empty_like(self.label_fake)
             self._label_stream = torch.cuda.Stream()
         self._labels_staged = self._labels_consumed = None
+        self.threaded_labels = threaded_labels and not device_labels
+        self._label_worker = self._label_future = None
+        # The labels come from a private generator that starts in the state of torch's CPU generator
+        # at construction: the sequence is the one make_D_label would draw in the reference loop
+        # (utils/utils.py:26-28) when nothing else consumes that generator, and a background draw
+        # can never interleave with other users of the global generator (DataLoader seeds, user code).
+        self._label_gen = torch.Generator()
+        self._label_gen.set_state(torch.get_rng_state())
         self._draw_labels(0)
         self._stage_labels()
         self._consume_labels()
@@ -622,7 +632,9 @@ class GraphedAdversarialSegStep:
         from . import _lib
         before = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: CUDA calls of other threads (another step object's label worker) must not
+        # invalidate this capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.losses = torch.stack(run())
         self.launches_per_step = _lib.launch_count() - before
 
@@ -680,8 +692,8 @@ class GraphedAdversarialSegStep:
         if self.label_draw is not None:
             self.label_draw(self.host_real[slot], self.host_fake[slot])
             return
-        self.host_real[slot].uniform_(0.7, 1.05)
-        self.host_fake[slot].uniform_(0.0, 0.305)
+        self.host_real[slot].uniform_(0.7, 1.05, generator=self._label_gen)
+        self.host_fake[slot].uniform_(0.0, 0.305, generator=self._label_gen)
 
     def _stage_labels(self):
         """Host slot -> device staging, on the label copy stream."""
@@ -718,12 +730,54 @@ class GraphedAdversarialSegStep:
         if batch_nogt is not None:
             for dst, src in zip(self.static_nogt, batch_nogt):
                 dst.copy_(src, non_blocking=True)
+        self._join_labels()                            # the draw + staging of this iteration's labels
         self._consume_labels()
         self.graph.replay()
         self._slot ^= 1
-        self._draw_labels(self._slot)                  # next iteration's labels, under the GPU's shadow
-        self._stage_labels()
+        self._next_labels()                            # next iteration's labels, under the GPU's shadow
         return self.losses
+
+    # Drawing 2 x B x N uniform floats from the CPU generator (the reference's semantics) takes about as
+    # long as the whole cfg5 step on the host (measured: 14 ms for 2 x 2^20 floats), so it must not sit
+    # on the launching thread: a single worker thread draws the next iteration's labels (ATen releases
+    # the GIL) and enqueues their copy to the device staging buffers; the launching thread only joins it
+    # right before it needs them.  One worker, strictly one draw after the other: the sequence of draws
+    # from the generator is the reference's (real, fake, real, fake, ...).
+    def _next_labels(self):
+        if self.device_labels:
+            return
+        if not self.threaded_labels:
+            self._draw_labels(self._slot)
+            self._stage_labels()
+            return
+        if self._label_worker is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._label_worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pcadv-labels")
+        dev = self.label_real.device
+
+        def job():
+            torch.cuda.set_device(dev)
+            self._draw_labels(self._slot)
+            self._stage_labels()
+        self._label_future = self._label_worker.submit(job)
+
+    def _join_labels(self):
+        fut, self._label_future = self._label_future, None
+        if fut is not None:
+            fut.result()
+
+    def close(self):
+        """Wait for the background label draw and release the worker thread."""
+        self._join_labels()
+        if self._label_worker is not None:
+            self._label_worker.shutdown(wait=True)
+            self._label_worker = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def run_testing_seg(dataloader, dataset, model, criterion, logger, test_iter, writer, args):
