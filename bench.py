@@ -574,6 +574,8 @@ def run_cuda_adv(args):
                        "max_rel_diff": rel, "tolerance": 1e-3}
         assert rel < 1e-3, "graph replay and eager step disagree: %s" % graph_check
 
+    if gstep is not None:
+        gstep.close()                              # no background label draw under the measurements below
     clouds = (Bg + Bn) * world * args.steps
     value = clouds / (ms / 1e3)
     e2e_value = clouds / (ms_e2e / 1e3)
