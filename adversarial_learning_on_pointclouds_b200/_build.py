@@ -6,7 +6,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libpcadv.so")
-SOURCES = ["api.cu", "simt_gemm.cu", "misc.cu", "head.cu", "tnet.cu", "metric.cu", "aux.cu", "tc_linear.cu", "tc_rows.cu", "tc_chain.cu", "tc_wgrad.cu", "tc_wgrad2.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "misc.cu", "head.cu", "tnet.cu", "metric.cu", "aux.cu", "tc_linear.cu", "tc_rows.cu", "tc_chain.cu", "tc_wgrad.cu", "tc_wgrad2.cu", "tc_level.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 

@@ -82,6 +82,16 @@ class ChainArgs(C.Structure):
                 ("rowmax_key", C.c_void_p), ("out_f32", C.c_void_p), ("n_f32", C.c_int32)]
 
 
+class BackLevelArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("n", C.c_int32), ("num_seg", C.c_int32), ("seg", Seg * MAX_SEG),
+                ("w", C.c_void_p), ("ldw", C.c_int64), ("x", C.c_void_p), ("ldx", C.c_int64),
+                ("mask_bits", C.c_void_p), ("ld_mask_bits", C.c_int64), ("mask_act", C.c_int32),
+                ("mask_slope", C.c_float), ("dz_out", C.c_void_p), ("ld_out", C.c_int64),
+                ("dw", C.c_void_p * MAX_SEG), ("ld_dw", C.c_int64 * MAX_SEG),
+                ("dbias", C.c_void_p * MAX_SEG), ("dgroup", C.c_void_p * MAX_SEG),
+                ("rows_per_group", C.c_int64), ("scale", C.c_void_p)]
+
+
 HEAD_CE, HEAD_LSM = 0, 1
 WS_MAXPOOL_BWD_INPLACE, WS_AMAX_SCALE = 0, 1
 
@@ -90,6 +100,7 @@ SYMBOLS = {
     "pcadv_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "pcadv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "pcadv_chain": (C.c_int, [C.POINTER(ChainArgs), C.c_void_p]),
+    "pcadv_backlevel": (C.c_int, [C.POINTER(BackLevelArgs), C.c_void_p]),
     "pcadv_max_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "pcadv_maxpool_bwd": (C.c_int, [C.POINTER(MaxBwdArgs), C.c_void_p]),

@@ -263,9 +263,21 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
     addends = addends or {}
     grads = [None] * len(layers)
     dz = dz_last
+    inv = scale2[1:2] if scale2 is not None else None
     for i in range(len(layers) - 1, -1, -1):
         L = layers[i]
         xin = x_segs if i == 0 else [ys[i - 1]]
+        if i > 0 and need_w[i] and need_b[i] and bits is not None and addends.get(i - 1) is None and \
+                ops.backlevel_eligible(prec, [dz.shape[1]], ys[i - 1], bits[i - 1]):
+            # one pass over dz: this layer's weight / bias gradient and the dz of the layer below
+            P = layers[i - 1]
+            wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz.shape[1]])
+            dw = _zeros(pool, (dz.shape[1], ys[i - 1].shape[1]), dz.device)
+            db = _zeros(pool, (dz.shape[1],), dz.device)
+            dz = ops.backlevel([dz], wt, ys[i - 1], mask_bits=bits[i - 1], mask_act=P.act, mask_slope=P.slope,
+                               dws=[dw], dbiases=[db], scale=inv)
+            grads[i] = (dw[:L.w.shape[0], :L.w.shape[1]], db[:L.w.shape[0]])
+            continue
         grads[i] = layer_wgrad(prec, dz, xin, L.w.shape, need_w[i], need_b[i], scale2, pool=pool)
         if i == 0:
             break

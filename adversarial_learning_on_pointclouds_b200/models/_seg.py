@@ -11,6 +11,8 @@ changes that leave the mathematics unchanged:
 * the backward through the max uses the saved argmax only (sparse scatter), and
   each trunk layer's dgrad is one GEMM over the K-concat [dz_next | dz_fc1].
 """
+import os
+
 import torch
 
 from .. import ops
@@ -23,6 +25,10 @@ PARAM_NAMES = tuple(n + s for n in _TRUNK + _HEAD for s in (".weight", ".bias"))
 _SLICES = ((0, 64), (64, 192), (192, 320), (320, 448), (448, 960))   # x1..x5 inside the concat
 _G0, _G1, _C1 = 960, 3008, 3024                                       # global / class columns
 
+
+# backward levels that run as one pcadv_backlevel launch (dgrad + the weight gradients of the layers the
+# level's activation feeds); the others keep separate dgrad / wgrad launches.  Tuning aid: PCADV_LEVELS.
+_LEVELS = frozenset(x for x in os.environ.get("PCADV_LEVELS", "fc4,fc3,l3,l2,l1").split(",") if x)
 
 HEAD_GAIN = 256.0        # the fused CE head stores 256 * (softmax - onehot) as the 16-bit dz
 
@@ -303,13 +309,25 @@ class SegFunction(torch.autograd.Function):
                                            (2048, 512), (512, 128), (128, 128), (128, 128), (128, 64),
                                            (64, 64)]), dev)
         # ---- head: fc4, fc3, fc2 ---------------------------------------------------
+        # A level = the dgrad through one stored activation + the weight gradients of the layers it
+        # feeds.  Where pcadv_backlevel takes the shape (and _LEVELS asks for it) both come out of one
+        # pass over dz; otherwise wgrad and dgrad are separate launches that each read dz.
+        inv_s = scale2[1:2] if scale2 is not None else None
         head = (("fc4", ACT_NONE), ("fc3", ACT_RELU), ("fc2", ACT_RELU))
         for li, (name, _) in enumerate(head):
             xin = hs[2 - li]
+            wt = dgrad_weight(prec, [W[name]], W[name].shape[1], [dz.shape[1]])
+            if name in _LEVELS and need[name + ".weight"] and need[name + ".bias"] and \
+                    ops.backlevel_eligible(prec, [dz.shape[1]], xin, hbits[2 - li]):
+                dw = pool.take(dz.shape[1], xin.shape[1])
+                db = pool.take(dz.shape[1])
+                dz = ops.backlevel([dz], wt, xin, mask_bits=hbits[2 - li], dws=[dw], dbiases=[db], scale=inv_s)
+                n_, k_ = W[name].shape
+                grads[name + ".weight"], grads[name + ".bias"] = dw[:n_, :k_], db[:n_]
+                continue
             dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
                                  need[name + ".bias"], scale2, pool=pool)
             grads[name + ".weight"], grads[name + ".bias"] = dw, db
-            wt = dgrad_weight(prec, [W[name]], W[name].shape[1], [dz.shape[1]])
             dz, _, _ = ops.linear([dz], wt, mask=xin, mask_act=ACT_RELU, out_dtype=prec.act_dtype,
                                   engine=prec.engine, mask_bits=hbits[2 - li])
         dz_fc1 = dz                                                   # [P, 256], scaled
@@ -319,8 +337,33 @@ class SegFunction(torch.autograd.Function):
         dw1 = pool.take(256, _C1) if need_w1 else None
         db1 = pool.take(256) if need_b1 else None
         dcb = pool.take(B, 256)                                        # d(cbias), scaled
-        ops.wgrad(dz_fc1, xs if need_w1 else [], dw=dw1[:, :_G0] if need_w1 else None,
-                  dgroup_bias=dcb, rows_per_group=N, scale=inv, engine=prec.engine)
+        # trunk levels that go through pcadv_backlevel also form their slice of fc1's weight gradient
+        # (dz_fc1^T x_k); fc1's own wgrad launch then covers the remaining x segments only
+        fused = [False] * 5
+        if need_w1:
+            for li in range(1, 5):                                     # level li: x_li feeds conv_{li+1} and fc1
+                name = _TRUNK[li]
+                fused[li - 1] = ("l%d" % li) in _LEVELS and need[name + ".weight"] and need[name + ".bias"] and \
+                    ops.backlevel_eligible(prec, [W[name].shape[0], dz_fc1.shape[1]], xs[li - 1], xbits[li - 1])
+        rest = [i for i in range(5) if not fused[i]]
+        if need_w1 and len(rest) == 5:
+            ops.wgrad(dz_fc1, xs, dw=dw1[:, :_G0], dgroup_bias=dcb, rows_per_group=N, scale=inv,
+                      engine=prec.engine)
+        else:
+            # runs of adjacent unfused segments share one launch (their dw columns are contiguous)
+            first = True
+            i = 0
+            while need_w1 and i < len(rest):
+                j = i
+                while j + 1 < len(rest) and rest[j + 1] == rest[j] + 1:
+                    j += 1
+                c0, c1 = _SLICES[rest[i]][0], _SLICES[rest[j]][1]
+                ops.wgrad(dz_fc1, [xs[q] for q in rest[i:j + 1]], dw=dw1[:, c0:c1],
+                          dgroup_bias=dcb if first else None, rows_per_group=N, scale=inv, engine=prec.engine)
+                first = False
+                i = j + 1
+            if first:                                                  # nothing left for fc1's own launch
+                ops.wgrad(dz_fc1, [], dgroup_bias=dcb, rows_per_group=N, scale=inv, engine=prec.engine)
         if need_w1 or need_b1:
             ops.wgrad(dcb, [g, cls2] if need_w1 else [], dw=dw1[:, _G0:_C1] if need_w1 else None,
                       dbias=db1, scale=inv)
@@ -354,12 +397,20 @@ class SegFunction(torch.autograd.Function):
         for li in range(4, 0, -1):                                    # conv5 .. conv2
             name = _TRUNK[li]
             xin = xs[li - 1]
-            dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
-                                 need[name + ".bias"], scale2, pool=pool)
-            grads[name + ".weight"], grads[name + ".bias"] = dw, db
             sl = _SLICES[li - 1]
             wt = dgrad_weight(prec, [W[name], W["fc1"][:, sl[0]:sl[1]]], W[name].shape[1],
                               [dz.shape[1], 256])
+            if fused[li - 1]:
+                dw = pool.take(dz.shape[1], xin.shape[1])
+                db = pool.take(dz.shape[1])
+                dz = ops.backlevel([dz, dz_fc1], wt, xin, mask_bits=xbits[li - 1],
+                                   dws=[dw, dw1[:, sl[0]:sl[1]]], dbiases=[db, None], scale=inv)
+                n_, k_ = W[name].shape
+                grads[name + ".weight"], grads[name + ".bias"] = dw[:n_, :k_], db[:n_]
+                continue
+            dw, db = layer_wgrad(prec, dz, [xin], W[name].shape, need[name + ".weight"],
+                                 need[name + ".bias"], scale2, pool=pool)
+            grads[name + ".weight"], grads[name + ".bias"] = dw, db
             dz, _, _ = ops.linear([dz, dz_fc1], wt, mask=xin, mask_act=ACT_RELU,
                                   out_dtype=prec.act_dtype, engine=prec.engine, mask_bits=xbits[li - 1])
         dw, db = layer_wgrad(prec, dz, [pts2], W["conv1"].shape, need["conv1.weight"],

@@ -336,6 +336,73 @@ def wgrad(dz, segs, *, dw=None, dbias=None, dgroup_bias=None, rows_per_group=0, 
         _call(tag, _lib.lib().pcadv_wgrad, C.byref(a), _stream(), rows=rows)
 
 
+_LEVEL_ON = os.environ.get("PCADV_LEVEL", "1") != "0"      # tuning aid: separate dgrad / wgrad launches
+
+
+def backlevel_eligible(prec, ks, x, mask_bits, rows_per_group=0, want_group=False):
+    """Shapes ``backlevel`` takes: tensor-core engine, 16-bit storage, the widths ``ks`` of the incoming
+    gradients and the width of ``x`` multiples of 64, sum(ks) small enough for the weight-gradient
+    accumulators to stay in TMEM beside one dgrad accumulator, the sign-bit map of x at hand."""
+    if not _LEVEL_ON or prec.engine != ENGINE_TC or prec.act_dtype == torch.float32 or mask_bits is None:
+        return False
+    rows, n = x.shape
+    if rows < 128 or n % 64 or x.dtype != prec.act_dtype or x.stride(0) % 8 or x.data_ptr() % 16:
+        return False
+    if any(k % 64 for k in ks) or len(ks) > _lib.MAX_SEG:
+        return False
+    if want_group and (rows_per_group <= 0 or rows_per_group % 128):
+        return False
+    # TMEM budget of tc_level.cu: (K / 128 weight-gradient tiles + one dgrad accumulator) x 64 columns
+    return (1 + (sum(ks) + 127) // 128) * 64 <= 512
+
+
+def backlevel(segs, w, x, *, mask_bits=None, mask_act=ACT_RELU, mask_slope=0.0, dws=None, dbiases=None,
+              dgroups=None, rows_per_group=0, scale=None, out=None):
+    """See ``pcadv_backlevel``: dz_out = act'(x) * ([segs] @ w^T) together with the weight gradients
+    ``dws[i] [k_i, n] += scale * segs[i]^T @ x``, ``dbiases[i] [k_i] += scale * colsum(segs[i])`` and the
+    per-cloud column sums ``dgroups[i] [rows / rows_per_group, k_i]`` in one pass over ``segs``.
+    Returns dz_out ([rows, n], the dtype of x)."""
+    a = _lib.BackLevelArgs()
+    rows, n = x.shape
+    a.rows, a.n, a.num_seg = rows, n, len(segs)
+    ktot = 0
+    for i, s in enumerate(segs):
+        if s.shape[0] != rows or s.dtype != x.dtype:
+            raise ValueError("segment %d: expected [%d, k] %s" % (i, rows, x.dtype))
+        p, ld, dt = _mat(s)
+        a.seg[i].ptr, a.seg[i].ld, a.seg[i].k, a.seg[i].dtype = p, ld, s.shape[1], dt
+        ktot += s.shape[1]
+    if tuple(w.shape) != (n, ktot) or w.dtype != x.dtype:
+        raise ValueError("weight %s does not match n=%d, ktot=%d" % (tuple(w.shape), n, ktot))
+    a.w, a.ldw, _ = _mat(w)
+    a.x, a.ldx, _ = _mat(x)
+    if mask_bits is not None and mask_act != ACT_NONE:
+        a.mask_bits, a.ld_mask_bits = C.c_void_p(mask_bits.data_ptr()), mask_bits.stride(0)
+        a.mask_act, a.mask_slope = mask_act, float(mask_slope)
+    dz = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
+    a.dz_out, a.ld_out, _ = _mat(dz)
+    for i, s in enumerate(segs):
+        dw = dws[i] if dws else None
+        if dw is not None:
+            p, ld, dt = _mat(dw)
+            if dt != F32 or dw.shape[0] < s.shape[1] or dw.shape[1] != n:
+                raise ValueError("dws[%d] must be fp32 [>=%d, %d], got %s" % (i, s.shape[1], n, tuple(dw.shape)))
+            a.dw[i], a.ld_dw[i] = p, ld
+        db = dbiases[i] if dbiases else None
+        if db is not None:
+            if db.numel() < s.shape[1]:
+                raise ValueError("dbiases[%d] needs %d elements" % (i, s.shape[1]))
+            a.dbias[i] = _f32(db)
+        dgp = dgroups[i] if dgroups else None
+        if dgp is not None:
+            a.dgroup[i] = _f32(dgp, (rows // rows_per_group) * s.shape[1])
+    a.rows_per_group = int(rows_per_group)
+    a.scale = _f32(scale) if scale is not None else None
+    if rows > 0:
+        _call("backlevel:k%d:n%d" % (ktot, n), _lib.lib().pcadv_backlevel, C.byref(a), _stream(), rows=rows)
+    return dz
+
+
 def max_finalize(key, act=ACT_NONE, slope=0.0, want_idx=True):
     """Unpack packed max keys -> (val fp32, idx int32) with the shape of ``key``."""
     val = torch.empty(key.shape, dtype=torch.float32, device=key.device)

@@ -395,7 +395,7 @@ def run_cuda_plain(args):
     sampler.join(timeout=2)
     peaks = _peaks()
     clouds = B * world * args.steps
-    rl = kernel_rooflines(ksum, float(B * N), peaks, args.steps, top=10)
+    rl = kernel_rooflines(ksum, float(B * N), peaks, args.steps, top=24)
     top = rl[0] if rl else None
     roofline = None
     if top is not None:
@@ -671,7 +671,7 @@ def run_cuda_adv(args):
     H.finish()
 
 
-def kernel_rooflines(ksum, points, peaks, steps, top=14, rows_of=None):
+def kernel_rooflines(ksum, points, peaks, steps, top=24, rows_of=None):
     """Achieved HBM GB/s and tensor TFLOP/s of the per-point kernels against the measured peaks,
     from their call signatures (algorithmic bytes / FLOPs per point: DESIGN.md 4), the rows each
     launch processed and their mean launch time (CUDA events on the launching stream)."""
@@ -696,6 +696,11 @@ def kernel_rooflines(ksum, points, peaks, steps, top=14, rows_of=None):
                 by = 2.0 * k + out_b + (n / 8.0 if n % 64 == 0 else 0.0)
                 if ":mask" in flags and "maskbits" not in flags:
                     by += 2.0 * n
+        elif tag.startswith("backlevel:"):
+            mm = re.match(r"backlevel:k(\d+):n(\d+)", tag)
+            k, n = int(mm.group(1)), int(mm.group(2))
+            by = 2.0 * k + 4.0 * n + n / 8.0                        # dz in, x in, dz out, sign bits
+            fl = 4.0 * k * n                                        # dgrad + weight gradients
         elif tag.startswith("chain:"):
             mm = re.match(r"chain:k(\d+):([\d-]+)(:rowmax)?", tag)
             widths = [int(v) for v in mm.group(2).split("-")]

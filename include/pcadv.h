@@ -178,6 +178,46 @@ typedef struct pcadv_wgrad_args {
 
 int pcadv_wgrad(const pcadv_wgrad_args* a, void* stream);
 
+/*
+ * pcadv_backlevel: one backward LEVEL of a pointwise chain in a single pass over the incoming
+ * gradient.  x is a stored activation; seg[i] are the gradients dz_i (w.r.t. the pre-activation
+ * outputs) of the layers that consumed x -- for PointNetSeg's trunk level k: dz_{k+1} and dz_fc1,
+ * because x_k feeds conv_{k+1} and, through the concat of models/pointnet.py:304-309, fc1:
+ *   dz_out[r, c]    = act'(x[r, c]) * sum_i sum_k seg_i[r, k] * w[c, koff_i + k]
+ *   dw[i][k, c]    += scale * sum_r seg_i[r, k] * x[r, c]        (= d(weight of consumer i)[k, c])
+ *   dbias[i][k]    += scale * sum_r seg_i[r, k]
+ *   dgroup[i][g, k] += sum_{r in cloud g} seg_i[r, k]            (NOT scaled; rows_per_group % 128 == 0)
+ * i.e. what autograd derives with one dgrad GEMM per level and one wgrad GEMM per consumer, each of
+ * which re-reads the dz matrices; here every dz tile is fetched once and feeds both tensor-core GEMMs.
+ * Tensor-core engine only: seg / w / x / dz_out share one 16-bit dtype, every k_i and n is a multiple
+ * of 64, sum k_i <= 1024, rows >= 128.  w = [n, sum k_i] (the K-concat of the transposed forward
+ * weights), mask_bits = the sign-bit map of x (see pcadv_linear), fp32 outputs are accumulated into.
+ */
+typedef struct pcadv_backlevel_args {
+  int64_t rows;
+  int32_t n;
+  int32_t num_seg;
+  pcadv_seg seg[PCADV_MAX_SEG];
+  const void* w;
+  int64_t ldw;
+  const void* x;              /* [rows, n] */
+  int64_t ldx;
+  const uint32_t* mask_bits;  /* [rows, ld_mask_bits] words or NULL with mask_act == PCADV_ACT_NONE */
+  int64_t ld_mask_bits;
+  int32_t mask_act;
+  float mask_slope;
+  void* dz_out;               /* [rows, n] */
+  int64_t ld_out;
+  float* dw[PCADV_MAX_SEG];   /* [k_i, n] or NULL */
+  int64_t ld_dw[PCADV_MAX_SEG];
+  float* dbias[PCADV_MAX_SEG];    /* [k_i] or NULL */
+  float* dgroup[PCADV_MAX_SEG];   /* [rows / rows_per_group, k_i] or NULL */
+  int64_t rows_per_group;
+  const float* scale;         /* device scalar or NULL */
+} pcadv_backlevel_args;
+
+int pcadv_backlevel(const pcadv_backlevel_args* a, void* stream);
+
 /* Unpack `count` packed max keys: val = act(value), idx = first index (0 when a
  * ReLU layer's maximum is <= 0, as every post-ReLU value then ties at 0 and
  * torch.max returns the first).  idx may be NULL. */

@@ -34,9 +34,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_ctypes_structs_match_c_layout():
-    code = '#include <stdio.h>\n#include "pcadv.h"\nint main(){printf("%zu %zu %zu %zu\\n",' \
+    code = '#include <stdio.h>\n#include "pcadv.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
            'sizeof(pcadv_seg),sizeof(pcadv_linear_args),sizeof(pcadv_wgrad_args),' \
-           'sizeof(pcadv_maxbwd_args));return 0;}\n'
+           'sizeof(pcadv_maxbwd_args),sizeof(pcadv_backlevel_args),sizeof(pcadv_chain_args),' \
+           'sizeof(pcadv_head_args));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c")
         open(c, "w").write(code)
@@ -44,7 +45,9 @@ def test_ctypes_structs_match_c_layout():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_lib.Seg), ctypes.sizeof(_lib.LinearArgs),
-                     ctypes.sizeof(_lib.WgradArgs), ctypes.sizeof(_lib.MaxBwdArgs)]
+                     ctypes.sizeof(_lib.WgradArgs), ctypes.sizeof(_lib.MaxBwdArgs),
+                     ctypes.sizeof(_lib.BackLevelArgs), ctypes.sizeof(_lib.ChainArgs),
+                     ctypes.sizeof(_lib.HeadArgs)]
 
 
 def test_header_is_plain_c():

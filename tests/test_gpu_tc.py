@@ -230,3 +230,60 @@ def test_tc_chain_wide_tail_with_fp32_logits(dtype, rows):
         assert torch.equal(outs[l], ref), l
         assert torch.equal(bits[l], bt), l
         cur = ref
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,ks,n,rpg,act", [
+    (1000, [128, 256], 128, 0, ACT_RELU),        # trunk level 2 / 3: one dgrad accumulator beside 3 weight tiles
+    (4133, [128, 256], 64, 0, ACT_RELU),         # level 1
+    (2560, [512, 256], 128, 0, ACT_RELU),        # level 4: two 64-column slices
+    (4096, [256], 512, 1024, ACT_RELU),          # level 5: four slices, per-cloud column sums
+    (3000, [256], 256, 0, ACT_LEAKY),            # fc2 level
+    (129, [128], 256, 0, ACT_RELU),              # fc3 level, ragged rows
+    (5000, [64], 128, 0, ACT_RELU),              # fc4 level: K = 64 zero-padded to one 128-channel tile
+    (40000, [512, 256, 128], 64, 0, ACT_NONE),   # K = 896: seven weight tiles + one accumulator = all of TMEM
+])
+def test_tc_backlevel(dtype, rows, ks, n, rpg, act):
+    """pcadv_backlevel = the dgrad GEMM of a level + the weight gradients of the layers fed by x +
+    bias / per-cloud sums, against fp64 torch on the same 16-bit operands."""
+    segs = [_rand((rows, k), 40 + i, dtype) for i, k in enumerate(ks)]
+    w = _rand((n, sum(ks)), 50, dtype, 0.1)
+    xpre = _rand((rows, n), 51, dtype)
+    x = F.leaky_relu(xpre, 0.2) if act == ACT_LEAKY else (xpre.relu() if act == ACT_RELU else xpre)
+    bits = None
+    if act != ACT_NONE:
+        # sign bits in the layout pcadv_linear writes: column 2 k at bit k, 2 k + 1 at bit 16 + k of word c // 32
+        pos = (x.float() > 0).reshape(rows, n // 32, 32).long()
+        j = torch.arange(32, device=DEV)
+        shifts = (j >> 1) + 16 * (j & 1)
+        words = (pos << shifts).sum(2)
+        bits = (words - ((words >> 31) << 32)).to(torch.int32).contiguous()
+    dws = [torch.zeros((k, n), device=DEV) for k in ks]
+    # column sums are taken for at most 8 chunks (512 channels) per launch
+    dbs, used = [], 0
+    for k in ks:
+        dbs.append(torch.zeros((k,), device=DEV) if used + k // 64 <= 8 else None)
+        used += k // 64 if dbs[-1] is not None else 0
+    groups = rows // rpg if rpg else 0
+    dgs = [torch.zeros((groups, k), device=DEV) if rpg and dbs[i] is not None else None for i, k in enumerate(ks)]
+    sc = torch.tensor([0.25], device=DEV)
+    dz = ops.backlevel(segs, w, x, mask_bits=bits, mask_act=act, mask_slope=0.2, dws=dws, dbiases=dbs,
+                       dgroups=dgs if rpg else None, rows_per_group=rpg, scale=sc)
+    torch.cuda.synchronize()
+    cat = torch.cat(segs, 1).double()
+    ref = cat @ w.double().t()
+    if act == ACT_RELU:
+        ref = ref * (x > 0)
+    elif act == ACT_LEAKY:
+        ref = torch.where(x > 0, ref, ref * 0.2)
+    tol = 1e-3 if dtype == torch.float16 else 6e-3
+    assert dz.dtype == dtype and rel_err(dz, ref) < tol
+    for i, s in enumerate(segs):
+        assert rel_err(dws[i], 0.25 * (s.double().t() @ x.double())) < 1e-5, i
+        if dbs[i] is not None:
+            assert rel_err(dbs[i], 0.25 * s.double().sum(0)) < 1e-5, i
+        if rpg and dgs[i] is not None:
+            assert rel_err(dgs[i], s.double().reshape(groups, rpg, -1).sum(1)) < 1e-5, i
+    # second call accumulates
+    ops.backlevel(segs, w, x, mask_bits=bits, mask_act=act, mask_slope=0.2, dws=dws, dbiases=dbs, scale=sc)
+    assert rel_err(dws[0], 0.5 * (segs[0].double().t() @ x.double())) < 1e-5

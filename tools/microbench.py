@@ -113,6 +113,31 @@ def cases(P, N):
     wg("wg_conv3", 128, [128])
     wg("wg_d2", 64, [64])
 
+    # fused backward levels (pcadv_backlevel): dgrad of the level + weight gradients of x's consumers
+    def lv(name, ks, n, group=False, nsum=1):
+        segs = [r16((P, k)) for k in ks]
+        w = r16((n, sum(ks)), 0.05)
+        x = r16((P, n)).relu_()
+        bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (P, n // 32), device=DEV, dtype=torch.int32)
+        dws = [torch.zeros((k, n), device=DEV) for k in ks]
+        dbs = [torch.zeros((k,), device=DEV) if i < nsum else None for i, k in enumerate(ks)]
+        dgs = [torch.zeros((B, k), device=DEV) if (group and i == 0) else None for i, k in enumerate(ks)]
+        s1 = torch.ones(1, device=DEV)
+        out = torch.empty((P, n), device=DEV, dtype=torch.float16)
+        nbytes = P * (2 * sum(ks) + 4 * n + n // 8)
+        c[name] = (lambda: ops.backlevel(segs, w, x, mask_bits=bits, dws=dws, dbiases=dbs, dgroups=dgs,
+                                         rows_per_group=N, scale=s1, out=out), nbytes, 4.0 * P * sum(ks) * n)
+
+    lv("lv_fc4", [64], 128)
+    lv("lv_fc3", [128], 256)
+    lv("lv_fc2", [256], 256)
+    lv("lv5", [256], 512, group=True, nsum=0)
+    lv("lv4", [512, 256], 128)
+    lv("lv3", [128, 256], 128)
+    lv("lv4_nosum", [512, 256], 128, nsum=0)
+    lv("lv3_nosum", [128, 256], 128, nsum=0)
+    lv("lv1", [128, 256], 64)
+
     # sparse max-pool backward (conv6): realistic argmax distribution from a real forward
     x5 = r16((P, 512)).relu_()
     w6 = r16((2048, 512), 0.05)
