@@ -107,6 +107,9 @@ def _compute_weight(prec, w32, k_list, n):
 
 
 _CHAIN_ON = os.environ.get("PCADV_CHAIN", "1") != "0"      # tuning aid: per-layer launches only
+# widest dz for which a backward level goes through pcadv_backlevel (one weight-gradient tile in TMEM;
+# wider levels measured slower than separate dgrad / wgrad launches, tools/level_ab.py)
+_LEVEL_MAX_K = int(os.environ.get("PCADV_LEVEL_MAX_K", "128"))
 
 
 def _chain_run(prec, x, run, rowmax=False, want_bits=True, last_f32=False):
@@ -268,7 +271,7 @@ def chain_backward(prec, dz_last, x_segs, ys, layers, need_w, need_b, need_x, sc
         L = layers[i]
         xin = x_segs if i == 0 else [ys[i - 1]]
         if i > 0 and need_w[i] and need_b[i] and bits is not None and addends.get(i - 1) is None and \
-                ops.backlevel_eligible(prec, [dz.shape[1]], ys[i - 1], bits[i - 1]):
+                dz.shape[1] <= _LEVEL_MAX_K and ops.backlevel_eligible(prec, [dz.shape[1]], ys[i - 1], bits[i - 1]):
             # one pass over dz: this layer's weight / bias gradient and the dz of the layer below
             P = layers[i - 1]
             wt = dgrad_weight(prec, [L.w], L.w.shape[1], [dz.shape[1]])

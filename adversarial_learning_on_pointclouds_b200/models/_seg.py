@@ -26,9 +26,14 @@ _SLICES = ((0, 64), (64, 192), (192, 320), (320, 448), (448, 960))   # x1..x5 in
 _G0, _G1, _C1 = 960, 3008, 3024                                       # global / class columns
 
 
-# backward levels that run as one pcadv_backlevel launch (dgrad + the weight gradients of the layers the
-# level's activation feeds); the others keep separate dgrad / wgrad launches.  Tuning aid: PCADV_LEVELS.
-_LEVELS = frozenset(x for x in os.environ.get("PCADV_LEVELS", "fc4,fc3,l3,l2,l1").split(",") if x)
+# Backward levels of PointNetSeg that run as one pcadv_backlevel launch (dgrad + the weight gradients of
+# the layers the level's activation feeds); the others keep separate dgrad / wgrad launches.  Measured
+# back to back at 2^21 points (tools/level_ab.py): the narrow head levels win (fc4 0.34 -> 0.27 ms, fc3
+# 0.55 -> 0.50 ms); fc2 (K = n = 256) and the trunk levels with the fc1 K-segment (K = 384 / 768) do not --
+# their weight-gradient tiles fill TMEM, so the level runs sliced or with one dgrad accumulator and a
+# two-slot ring, and it loses to two launches that each stream at the HBM rate.  Tuning aid: PCADV_LEVELS
+# (e.g. "fc4,fc3,fc2,l4,l3,l2,l1").
+_LEVELS = frozenset(x for x in os.environ.get("PCADV_LEVELS", "fc4,fc3").split(",") if x)
 
 HEAD_GAIN = 256.0        # the fused CE head stores 256 * (softmax - onehot) as the 16-bit dz
 
