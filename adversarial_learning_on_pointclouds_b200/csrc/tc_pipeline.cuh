@@ -26,6 +26,7 @@ struct TensorMaps {
   CUtensorMap w;                    // weights [n, ktot]  (wgrad: dz [rows, n])
   CUtensorMap out;                  // output [rows, n]: box 128 rows x 128 B (TMA store)
   CUtensorMap mask;                 // saved activation [rows, n]: box 128 rows x 64 cols (TMA load)
+  CUtensorMap w_half;               // weights, box of bn / 2 rows: one CTA's share of a multicast weight tile
 };
 
 struct SharedTail {

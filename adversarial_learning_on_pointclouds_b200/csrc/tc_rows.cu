@@ -44,6 +44,8 @@ struct RowsParams {
   int64_t tiles_m, tiles_n;
   uint32_t idesc;
   int nstages, nslabs, stage_bytes;
+  int pair;               // CTA pairs (cluster of 2): each CTA fetches half of a weight tile and multicasts it to both
+  int epi_halves;         // lean kernel: 2 = two epilogue halves (one TMEM buffer each), 1 = one half drains both
   // epilogue
   const float* bias;
   const float* group_bias;
@@ -80,14 +82,14 @@ __device__ __forceinline__ RowsSmem carve_rows(uint8_t* raw, const RowsParams& p
   RowsSmem L;
   L.stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   L.epi = L.stages + p.nstages * p.stage_bytes;
-  L.bias = reinterpret_cast<float*>(L.epi + kEpiWarps * p.nslabs * kWarpSlabBytes);
+  L.bias = reinterpret_cast<float*>(L.epi + (p.epi_halves == 1 ? 4 : kEpiWarps) * p.nslabs * kWarpSlabBytes);
   L.bits = reinterpret_cast<uint32_t*>(L.bias + kRowsBiasFloats);
   L.tail = reinterpret_cast<RowsTail*>(reinterpret_cast<uint8_t*>(L.bits) + kBitsBytes);
   return L;
 }
 
-static size_t rows_smem_bytes(int nstages, int stage_bytes, int nslabs) {
-  return 1024 + static_cast<size_t>(nstages) * stage_bytes + kEpiWarps * nslabs * kWarpSlabBytes +
+static size_t rows_smem_bytes(int nstages, int stage_bytes, int nslabs, int epi_warps = kEpiWarps) {
+  return 1024 + static_cast<size_t>(nstages) * stage_bytes + epi_warps * nslabs * kWarpSlabBytes +
          kRowsBiasFloats * 4 + kBitsBytes + sizeof(RowsTail) + 16;
 }
 
@@ -117,9 +119,11 @@ __device__ __forceinline__ uint32_t rows_setup(const TensorMaps& maps, const Row
     tma_prefetch_desc(&maps.w);
     if (p.tma_out) tma_prefetch_desc(&maps.out);
     if (p.tma_mask) tma_prefetch_desc(&maps.mask);
+    if (p.pair) tma_prefetch_desc(&maps.w_half);
     for (int i = 0; i < kRowsMaxStages; ++i) {
       mbar_init(&st->full[i], 1);
-      mbar_init(&st->empty[i], 1);
+      // pairs: a stage is refilled (partly by the peer's multicast) once BOTH CTAs have consumed it
+      mbar_init(&st->empty[i], p.pair ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&st->tmem_full[i], 1);
@@ -132,19 +136,48 @@ __device__ __forceinline__ uint32_t rows_setup(const TensorMaps& maps, const Row
   if (warp == 1) tmem_alloc(&st->tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_barrier_sync();                 // the peer's barriers exist before anything is sent to them
   tc_fence_after();
   return st->tmem_base;
 }
 
+// Work items of a CTA.  Single CTAs walk the (row tile, column tile) list with stride gridDim.x.  In pair
+// mode the two CTAs of a cluster take the row tiles 2 i and 2 i + 1 of the same column tile side by side
+// (same weight tile, fetched once per pair), and pairs walk the list of row-tile PAIRS.
+struct RowsWork {
+  int64_t first, stride, count, tiles_n;
+  int pair, rank;
+  __device__ __forceinline__ int64_t tm(int64_t t) const { return pair ? 2 * (t / tiles_n) + rank : t / tiles_n; }
+  __device__ __forceinline__ int64_t tn(int64_t t) const { return t % tiles_n; }
+};
+__device__ __forceinline__ RowsWork rows_work(const RowsParams& p) {
+  RowsWork w;
+  w.pair = p.pair;
+  w.tiles_n = p.tiles_n;
+  if (p.pair) {
+    w.rank = static_cast<int>(cluster_cta_rank());
+    w.first = blockIdx.x >> 1;
+    w.stride = gridDim.x >> 1;
+    w.count = ((p.tiles_m + 1) >> 1) * p.tiles_n;
+  } else {
+    w.rank = 0;
+    w.first = blockIdx.x;
+    w.stride = gridDim.x;
+    w.count = p.tiles_m * p.tiles_n;
+  }
+  return w;
+}
+
 __device__ __forceinline__ void rows_producer(const TensorMaps& maps, const RowsParams& p,
                                               const RowsSmem& L, RowsTail* st, int64_t num_tiles) {
+  const RowsWork wk = rows_work(p);
   const uint32_t stage_tx = static_cast<uint32_t>((kTileM + p.bn) * kBlockK * 2);
+  const int half_rows = p.bn >> 1;
   int stage = 0;
   uint32_t phase = 0;
-  for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-    const int64_t tm = t / p.tiles_n, tn = t % p.tiles_n;
-    const int32_t m0 = static_cast<int32_t>(tm * kTileM);
-    const int32_t n0 = static_cast<int32_t>(tn * p.bn);
+  for (int64_t t = wk.first; t < wk.count; t += wk.stride) {
+    const int32_t m0 = static_cast<int32_t>(wk.tm(t) * kTileM);   // past the last row in an odd tail: zero fill
+    const int32_t n0 = static_cast<int32_t>(wk.tn(t) * p.bn);
     int kg = 0;
     for (int s = 0; s < p.num_seg; ++s) {
       for (int kk = 0; kk < p.seg_k[s]; kk += kBlockK, kg += kBlockK) {
@@ -152,7 +185,11 @@ __device__ __forceinline__ void rows_producer(const TensorMaps& maps, const Rows
         mbar_arrive_expect_tx(&st->full[stage], stage_tx);
         uint8_t* sa = L.stages + stage * p.stage_bytes;
         tma_load_2d(sa, &maps.act[s], &st->full[stage], kk, m0);
-        tma_load_2d(sa + kABytes, &maps.w, &st->full[stage], kg, n0);
+        if (p.pair)      // this CTA's half of the weight tile, delivered to both CTAs of the pair
+          tma_load_2d_multicast(sa + kABytes + wk.rank * half_rows * 128, &maps.w_half, &st->full[stage], kg,
+                                n0 + wk.rank * half_rows, 3);
+        else
+          tma_load_2d(sa + kABytes, &maps.w, &st->full[stage], kg, n0);
         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
       }
     }
@@ -161,13 +198,14 @@ __device__ __forceinline__ void rows_producer(const TensorMaps& maps, const Rows
 
 __device__ __forceinline__ void rows_mma(const RowsParams& p, const RowsSmem& L, RowsTail* st,
                                          uint32_t tmem_base, int64_t num_tiles) {
+  const RowsWork wk = rows_work(p);
   int total_chunks = 0;
   for (int s = 0; s < p.num_seg; ++s) total_chunks += p.seg_k[s] / kBlockK;
   int stage = 0;
   uint32_t phase = 0;
   int buf = 0;
   uint32_t buf_phase = 0;
-  for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+  for (int64_t t = wk.first; t < wk.count; t += wk.stride) {
     mbar_wait_backoff(&st->tmem_empty[buf], buf_phase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kMaxTileN);
@@ -176,7 +214,8 @@ __device__ __forceinline__ void rows_mma(const RowsParams& p, const RowsSmem& L,
       tc_fence_after();
       const uint32_t a_addr = smem_u32(L.stages + stage * p.stage_bytes);
       mma_chunk_kmajor(d_tmem, a_addr, a_addr + kABytes, p.idesc, c == 0);
-      umma_commit(&st->empty[stage]);
+      if (p.pair) umma_commit_multicast(&st->empty[stage], 3);
+      else umma_commit(&st->empty[stage]);
       if (++stage == p.nstages) { stage = 0; phase ^= 1; }
     }
     umma_commit(&st->tmem_full[buf]);
@@ -184,9 +223,10 @@ __device__ __forceinline__ void rows_mma(const RowsParams& p, const RowsSmem& L,
   }
 }
 
-__device__ __forceinline__ void rows_teardown(int warp, uint32_t tmem_base) {
+__device__ __forceinline__ void rows_teardown(int warp, uint32_t tmem_base, int pair = 0) {
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_barrier_sync();                   // the peer may still signal this CTA's barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -262,8 +302,10 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
     const int steps = p.bn >> 6;                          // bn is a multiple of 64 here
     const int tiles_n = static_cast<int>(p.tiles_n);
     const int n = p.n, bn = p.bn;
-    const uint32_t slab0 = smem_u32(L.epi + ew * 2 * kWarpSlabBytes) + lane * 128;   // two slabs
-    const uint32_t slab_tma0 = smem_u32(L.epi + ew * 2 * kWarpSlabBytes);
+    const int halves = p.epi_halves;                      // 1: this half (0) drains both TMEM buffers
+    const int nslabs = p.nslabs;
+    const uint32_t slab0 = smem_u32(L.epi + ew * nslabs * kWarpSlabBytes) + lane * 128;
+    const uint32_t slab_tma0 = smem_u32(L.epi + ew * nslabs * kWarpSlabBytes);
     const uint32_t bits_s = smem_u32(L.bits + ew * 32 * kBitsWords);
     float* bias_s = L.bias + half * 3 * kMaxTileN;
     const uint32_t bias_a = smem_u32(bias_s);
@@ -281,10 +323,11 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
     uint2 mbw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbw[i] = make_uint2(0u, 0u);
+    const RowsWork wk = rows_work(p);
     auto fetch_bits = [&](int64_t tt) {
-      if (tt >= num_tiles) return;
-      const int64_t ttm = tt / tiles_n;
-      const int ttn = static_cast<int>(tt - ttm * tiles_n);
+      if (tt >= wk.count) return;
+      const int64_t ttm = wk.tm(tt);
+      const int ttn = static_cast<int>(wk.tn(tt));
       const int64_t rr = ttm * kTileM + lane_row;
       if (rr >= p.rows) return;
       const uint2* src = reinterpret_cast<const uint2*>(p.mask_bits + rr * p.ld_mask_bits + ((ttn * bn) >> 5));
@@ -292,18 +335,20 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
       for (int i = 0; i < 4; ++i)
         if (i < steps) mbw[i] = __ldg(src + i);
     };
-    if (kMaskBits) fetch_bits(blockIdx.x + static_cast<int64_t>(half) * gridDim.x);
-    for (int64_t t = blockIdx.x + static_cast<int64_t>(half) * gridDim.x; t < num_tiles;
-         t += 2 * static_cast<int64_t>(gridDim.x), ++use) {
-      const int64_t tm = t / tiles_n;
-      const int tn = static_cast<int>(t - tm * tiles_n);
+    const int64_t t_begin = half < halves ? wk.first + static_cast<int64_t>(half) * wk.stride : wk.count;
+    const int64_t t_stride = static_cast<int64_t>(halves) * wk.stride;
+    if (kMaskBits) fetch_bits(t_begin);
+    for (int64_t t = t_begin; t < wk.count; t += t_stride, ++use) {
+      const int64_t tm = wk.tm(t);
+      const int tn = static_cast<int>(wk.tn(t));
       const int64_t r = tm * kTileM + lane_row;
       const bool r_ok = r < p.rows;
       const int col_base = tn * bn;
       const int32_t row_tma = static_cast<int32_t>(tm * kTileM + quarter * 32);
       uint32_t gsel = 0;                                  // byte offset of this row's per-cloud bias
       if (kAdd != kAddNone) {
-        const int64_t row_first = tm * kTileM;
+        // (a pair's odd tail tile lies past the last row: it stages the last cloud's bias and stores nothing)
+        const int64_t row_first = tm * kTileM < p.rows ? tm * kTileM : p.rows - 1;
         const int64_t row_last = row_first + kTileM - 1 < p.rows ? row_first + kTileM - 1 : p.rows - 1;
         const int64_t g_first = row_first / rpg, g_last = row_last / rpg;
         const bool restage = col_base != staged_col ||
@@ -328,19 +373,23 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
       uint2 mbc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) mbc[i] = mbw[i];
-      if (kMaskBits) fetch_bits(t + 2 * static_cast<int64_t>(gridDim.x));
-      mbar_wait(&st->tmem_full[half], use & 1);
+      if (kMaskBits) fetch_bits(t + t_stride);
+      const int buf = halves == 2 ? half : static_cast<int>(use & 1);
+      mbar_wait(&st->tmem_full[buf], halves == 2 ? (use & 1) : ((use >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                              static_cast<uint32_t>(half * kMaxTileN);
+                              static_cast<uint32_t>(buf * kMaxTileN);
       float best = -INFINITY;                             // kRowMax: running (max, first column)
       int best_col = 0;
 #pragma unroll 1
       for (int step = 0; step < steps; ++step) {
         const uint32_t srow = slab0 + slab * kWarpSlabBytes;
         if (!kRowMax) {
-          // the store that last read this slab (two steps ago) is done with it
-          if (lane == 0) bulk_wait_group_read<1>();
+          // the store that last read this slab (two steps ago; the previous one with one slab) is done with it
+          if (lane == 0) {
+            if (nslabs == 2) bulk_wait_group_read<1>();
+            else bulk_wait_group_read<0>();
+          }
           __syncwarp();
         }
         uint32_t raw[2][32];
@@ -426,7 +475,7 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
           tma_store_2d_addr(&maps.out, slab_tma0 + slab * kWarpSlabBytes, col_base + step * 64, row_tma);
           bulk_commit_group();
         }
-        slab ^= 1;
+        if (nslabs == 2) slab ^= 1;
       }
       if (kRowMax && r_ok) {
         const unsigned long long key = pack_key(best, static_cast<uint32_t>(best_col));
@@ -450,11 +499,11 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&st->tmem_empty[half]);
+      if (lane == 0) mbar_arrive(&st->tmem_empty[buf]);
     }
     if (lane == 0) bulk_wait_group<0>();
   }
-  rows_teardown(warp, tmem_base);
+  rows_teardown(warp, tmem_base, p.pair);
 }
 
 typedef void (*RowsKernel)(const TensorMaps, const RowsParams);
@@ -866,15 +915,67 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
                    (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && (a.n * esz) % 4 == 0 &&
                    32 * a.n * esz <= p.nslabs * kWarpSlabBytes) ? 1 : 0;
   p.stage_bytes = kABytes + p.bn * kBlockK * 2;
+  p.epi_halves = 2;
   int nst = kRowsMaxStages;
   while (nst > 2 && rows_smem_bytes(nst, p.stage_bytes, p.nslabs) > static_cast<size_t>(kRowsSmemMax)) --nst;
+  int epi_warps = kEpiWarps;
+  if (lean && lean != lean_rowmax() && ktot >= 512) {
+    // Deep-K layers (fc1: K = 960): a tile's MMAs take several microseconds, so ONE epilogue half with one
+    // slab per warp keeps up with both TMEM buffers, and the 48 KB it frees is one more ring stage
+    // (measured: fc1 0.564 -> 0.555 ms, the K = 768 dgrad 0.324 -> 0.313 ms per 2^20 points).
+    static int deep = -1;
+    if (deep < 0) { const char* e = getenv("PCADV_ROWS_DEEP"); deep = (e && atoi(e) == 0) ? 0 : 1; }   // tuning aid
+    int nst1 = kRowsMaxStages;
+    while (nst1 > 2 && rows_smem_bytes(nst1, p.stage_bytes, 1, 4) > static_cast<size_t>(kRowsSmemMax)) --nst1;
+    if (deep && nst1 > nst) { nst = nst1; p.epi_halves = 1; p.nslabs = 1; epi_warps = 4; }
+  }
   p.nstages = nst;
-  const size_t smem = rows_smem_bytes(p.nstages, p.stage_bytes, p.nslabs);
+  const size_t smem = rows_smem_bytes(p.nstages, p.stage_bytes, p.nslabs, epi_warps);
   PCADV_CHECK_ARG(smem <= static_cast<size_t>(kRowsSmemMax), "tc_linear: shared memory budget exceeded");
   const int64_t tiles = p.tiles_m * p.tiles_n;
-  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   RowsKernel k = lean ? lean : pick_rows_kernel(a.act, out_dt);
   if (int rc = ensure_rows_smem(reinterpret_cast<const void*>(k))) return rc;
+  // ---- CTA pairs for wide weight tiles (PCADV_ROWS_PAIR=1; off by default).  Every 128-row tile streams the
+  // layer's whole weight tile from L2 (fc1: 480 KB next to 240 KB of activations, ~11 TB/s out of the L2
+  // slices at 2^20 points).  Two CTAs of a cluster take two row tiles of the same column tile side by side,
+  // each fetches HALF of every weight chunk and TMA multicasts it into both, so the slices serve each weight
+  // byte once per 256 rows.  Measured: fc1 alone 0.529 -> 0.509 ms per 2^20 points, the other layers
+  // unchanged, the cfg5 step 15.42 -> 15.54 ms (cluster launches next to the discriminator branch of the
+  // graph) -- fc1 runs at 1.0 PFLOP/s and 5.0 TB/s at once, i.e. against the power cap, not the L2.
+  static int pair_mode = -1;
+  if (pair_mode < 0) { const char* e = getenv("PCADV_ROWS_PAIR"); pair_mode = e ? atoi(e) : 0; }   // 0 off, 1 wide weight tiles, 2 all lean launches
+  const bool wide_w = static_cast<int64_t>(ktot) * p.bn >= 256 * 256;
+  if (lean && lean != lean_rowmax() && pair_mode > 0 && (wide_w || pair_mode == 2) && p.bn % 16 == 0 &&
+      p.tiles_m >= 4 && num_sms() >= 2) {
+    if (int rc = encode_tmap_2d(&maps.w_half, a.w, dt, a.n, ktot, a.ldw, kBlockK, p.bn / 2)) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kRowsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    // clusters that can be resident at once (a GPC with an odd SM count leaves one SM unpaired)
+    static int max_pairs = -1;
+    if (max_pairs < 0) {
+      cfg.gridDim = dim3(num_sms() / 2 * 2);
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, reinterpret_cast<const void*>(k), &cfg) != cudaSuccess || nc <= 0) {
+        cudaGetLastError();
+        nc = 0;
+      }
+      max_pairs = nc < num_sms() / 2 ? nc : num_sms() / 2;
+    }
+    const int64_t pair_items = ((p.tiles_m + 1) / 2) * p.tiles_n;
+    const int pairs = static_cast<int>(pair_items < max_pairs ? pair_items : max_pairs);
+    if (pairs >= 1) {
+      p.pair = 1;
+      cfg.gridDim = dim3(2 * pairs);
+      PCADV_CUDA_OK(cudaLaunchKernelEx(&cfg, k, maps, p));
+      PCADV_LAUNCHED();
+      return 0;
+    }
+  }
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   k<<<grid, kRowsThreads, smem, s>>>(maps, p);
   PCADV_LAUNCHED();
   return 0;
