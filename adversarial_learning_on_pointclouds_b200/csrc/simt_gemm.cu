@@ -526,17 +526,16 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const pcadv_wgra
 #pragma unroll
     for (int k = 0; k <= K; ++k) acc[i][k] = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x / groups;
-  for (int64_t r = tid / groups; r < a.rows; r += stride) {
-    float xv[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) xv[k] = __ldg(x + r * a.seg[0].ld + k);
-    float dz[8];
+  // kU rows per trip with every load issued before the first FMA: the kernel is latency-bound (one
+  // 16-byte load per row and thread), so the loads in flight per thread are what sets its rate
+  constexpr int kU = 4;
+  auto load_dz = [&](int64_t r, float (&dz)[8]) {
     if (a.dz_dtype == PCADV_F32) {
       const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dz) + r * a.ld_dz + cg);
       const float4 u = p[0], v = p[1];
       dz[0] = u.x; dz[1] = u.y; dz[2] = u.z; dz[3] = u.w; dz[4] = v.x; dz[5] = v.y; dz[6] = v.z; dz[7] = v.w;
     } else {
-      const uint4 t4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.dz) + r * a.ld_dz + cg);
+      const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.dz) + r * a.ld_dz + cg));
       const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -546,6 +545,49 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const pcadv_wgra
         dz[2 * e] = f.x; dz[2 * e + 1] = f.y;
       }
     }
+  };
+  int64_t r = tid / groups;
+  for (; r + (kU - 1) * stride < a.rows; r += kU * stride) {
+    float xv[kU][K];
+    uint4 raw[kU];
+    if (a.dz_dtype != PCADV_F32) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.dz) + (r + u * stride) * a.ld_dz + cg));
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+#pragma unroll
+      for (int k = 0; k < K; ++k) xv[u][k] = __ldg(x + (r + u * stride) * a.seg[0].ld + k);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float dz[8];
+      if (a.dz_dtype == PCADV_F32) {
+        load_dz(r + u * stride, dz);
+      } else {
+        const uint32_t w4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f;
+          if (a.dz_dtype == PCADV_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+          else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+          dz[2 * e] = f.x; dz[2 * e + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[i][k] = fmaf(dz[i], xv[u][k], acc[i][k]);
+        acc[i][K] += dz[i];
+      }
+    }
+  }
+  for (; r < a.rows; r += stride) {
+    float xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = __ldg(x + r * a.seg[0].ld + k);
+    float dz[8];
+    load_dz(r, dz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -743,7 +785,7 @@ int launch_colsum(const void* dz, int dz_dtype, int64_t ld, int64_t rows, int n,
 
 int simt_wgrad(const pcadv_wgrad_args& a, cudaStream_t s) {
   if ((a.dw || a.dbias) && first_layer_wgrad_eligible(a)) {
-    const unsigned blocks = 148 * 4;
+    const unsigned blocks = 148 * 3;      // 80 registers x 256 threads: three CTAs per SM, one wave
     switch (a.seg[0].k) {
       case 1: first_layer_wgrad_kernel<1><<<blocks, 256, 0, s>>>(a); break;
       case 2: first_layer_wgrad_kernel<2><<<blocks, 256, 0, s>>>(a); break;
