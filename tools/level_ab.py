@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 21)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--rounds", type=int, default=4)
+    ap.add_argument("--only-head", action="store_true", help="the single-segment levels only (ncu captures)")
     args = ap.parse_args()
     P, N = args.points, 4096
     torch.manual_seed(0)
@@ -87,6 +88,8 @@ def main():
     cases = [("trunk levels 3,2,1 + fc1 wgrad", old, new), pair("fc4 level k64 n128", 64, 128, P),
              pair("fc3 level k128 n256", 128, 256, P), pair("fc2 level k256 n256", 256, 256, P),
              pair("disc level k64 n64", 64, 64, P // 2)]
+    if args.only_head:
+        cases = cases[1:]
     for name, o, nw in cases:
         o(); nw()
         torch.cuda.synchronize()
