@@ -85,7 +85,29 @@ def main():
             ops.backlevel([dz], wt, x, mask_bits=bt, dws=[dw], dbiases=[db], scale=s1)
         return name, o, nw
 
-    cases = [("trunk levels 3,2,1 + fc1 wgrad", old, new), pair("fc4 level k64 n128", 64, 128, P),
+    def rowmax_case(rows):
+        """backward of the discriminator's conv4 (64 -> 128) + ReLU + max over channels and the dgrad to conv3"""
+        n, k = 128, 64
+        dy = torch.randn(rows, device=DEV)
+        val = torch.rand(rows, device=DEV)
+        idx = torch.randint(0, n, (rows,), device=DEV, dtype=torch.int32)
+        y = r16((rows, k)).relu_()
+        bt = torch.randint(-2 ** 31, 2 ** 31 - 1, (rows, k // 32), device=DEV, dtype=torch.int32)
+        w = r16((n, k), 0.1)
+        wt = w.t().contiguous()
+        dw = torch.zeros((n, k), device=DEV)
+        db = torch.zeros((n,), device=DEV)
+
+        def o():
+            ops.rowmax_wgrad(dy, val, idx, y, n, act=ACT_RELU, dw=dw, dbias=db)
+            ops.rowmax_dgrad(dy, val, idx, w, y, act=ACT_RELU, scale=s1, prev_act=ACT_RELU, out_dtype=torch.float16)
+
+        def nw():
+            dz = ops.rowmax_bwd(dy, val, idx, n, act=ACT_RELU, scale=s1, out_dtype=torch.float16)
+            ops.backlevel([dz], wt, y, mask_bits=bt, dws=[dw], dbiases=[db], scale=s1)
+        return "rowmax level n128 k64 (gather | one-hot)", o, nw
+
+    cases = [("trunk levels 3,2,1 + fc1 wgrad", old, new), rowmax_case(P // 2), pair("fc4 level k64 n128", 64, 128, P),
              pair("fc3 level k128 n256", 128, 256, P), pair("fc2 level k256 n256", 256, 256, P),
              pair("disc level k64 n64", 64, 64, P // 2)]
     if args.only_head:
