@@ -89,7 +89,9 @@ class BackLevelArgs(C.Structure):
                 ("mask_slope", C.c_float), ("dz_out", C.c_void_p), ("ld_out", C.c_int64),
                 ("dw", C.c_void_p * MAX_SEG), ("ld_dw", C.c_int64 * MAX_SEG),
                 ("dbias", C.c_void_p * MAX_SEG), ("dgroup", C.c_void_p * MAX_SEG),
-                ("rows_per_group", C.c_int64), ("scale", C.c_void_p)]
+                ("rows_per_group", C.c_int64), ("scale", C.c_void_p),
+                ("onehot_dy", C.c_void_p), ("onehot_val", C.c_void_p), ("onehot_idx", C.c_void_p),
+                ("onehot_act", C.c_int32), ("onehot_slope", C.c_float), ("onehot_scale", C.c_void_p)]
 
 
 HEAD_CE, HEAD_LSM = 0, 1

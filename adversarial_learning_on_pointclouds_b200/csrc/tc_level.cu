@@ -31,17 +31,20 @@ constexpr int kLvMaxChunks = 16;                 // K <= 1024 channels of dz per
 constexpr int kLvMaxSum = 8;                     // chunks whose column sums are taken
 constexpr int kLvSmemMax = 232448;
 constexpr int kLvSlabBytes = 32 * 128;
+constexpr int kLvMaxXBuf = 4;                     // x tiles in flight
+constexpr int kLvOneHotMax = 256;                // pooled channels of a one-hot segment
 
 struct LvTail {
   uint64_t full[kLvMaxStages];
   uint64_t empty[kLvMaxStages];
-  uint64_t x_full[2];
-  uint64_t x_empty[2];
+  uint64_t x_full[kLvMaxXBuf];
+  uint64_t x_empty[kLvMaxXBuf];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t w_full;
   uint64_t wres_full;
   uint32_t tmem_base;
+  float hist[kLvOneHotMax];         // one-hot mode: bias gradient per pooled channel
 };
 
 struct LvMaps {
@@ -61,7 +64,7 @@ struct LvParams {
   int chunk_sum[kLvMaxChunks];      // slot of its column sums, -1 = none
   int nsum;
   int pad_seg, pad_k0, pad_kg;      // coordinates outside the tensors: TMA fills zeros
-  int nstages, stage_bytes, nbuf, nslabs, epi_warps;
+  int nstages, stage_bytes, nbuf, nslabs, epi_warps, nxbuf;
   int wres;                         // the slice's dgrad weight stays resident in shared memory (loaded once)
   uint32_t idesc_d, idesc_w;
   int bf16;
@@ -76,6 +79,13 @@ struct LvParams {
   int64_t rows_per_group;
   const float* scale;
   int vec_red;
+  // one-hot mode: segment 0 is generated in shared memory (see pcadv_backlevel_args)
+  const float* oh_dy;
+  const float* oh_val;
+  const int32_t* oh_idx;
+  int oh_act;
+  float oh_slope;
+  const float* oh_scale;
   int dbg;                          // tuning aid (PCADV_LEVEL_DBG): 1 = no wgrad MMAs, 2 = no dgrad MMAs, 4 = spinning waits
 };
 
@@ -117,7 +127,7 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
   uint8_t* wres = stages + p.nstages * p.stage_bytes;               // [nchunks][bn rows][64 k] when resident
   const int wchunk_bytes = p.bn * 128;
   uint8_t* xt = wres + (p.wres ? p.nchunks * wchunk_bytes : 0);
-  uint8_t* epi = xt + 2 * x_bytes;
+  uint8_t* epi = xt + p.nxbuf * x_bytes;
   LvTail* st = reinterpret_cast<LvTail*>(epi + p.epi_warps * p.nslabs * kLvSlabBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,23 +137,26 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
   const int n0 = slice * p.bn;
   const int bn = p.bn;
   const int nchunks = p.nchunks;
-  const bool sums = p.nsum > 0 && slice == 0;
+  const bool onehot = p.oh_idx != nullptr;
+  const bool sums = !onehot && p.nsum > 0 && slice == 0;
   const uint32_t wbase = static_cast<uint32_t>(p.nbuf * bn);       // first weight-gradient column
   const bool spin = (p.dbg & 4) != 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < PCADV_MAX_SEG; ++s)
-      if (p.seg_k[s] > 0) tma_prefetch_desc(&maps.seg[s]);
+      if (p.seg_k[s] > 0 && p.oh_idx == nullptr) tma_prefetch_desc(&maps.seg[s]);
     tma_prefetch_desc(&maps.w);
     tma_prefetch_desc(&maps.x);
     tma_prefetch_desc(&maps.out);
     for (int i = 0; i < kLvMaxStages; ++i) {
-      mbar_init(&st->full[i], 1);
+      mbar_init(&st->full[i], onehot ? 4 : 1);     // TMA bytes, or the four generator warps
       mbar_init(&st->empty[i], sums ? 5 : 1);     // MMA commit (+ the four column-sum warps)
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kLvMaxXBuf; ++i) {
       mbar_init(&st->x_full[i], 1);
       mbar_init(&st->x_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&st->tmem_full[i], 1);
       mbar_init(&st->tmem_empty[i], 4);
     }
@@ -152,6 +165,8 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&st->tmem_base, kTmemCols);
+  if (onehot)
+    for (int i = threadIdx.x; i < kLvOneHotMax; i += kLvThreads) st->hist[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -180,8 +195,8 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
         __syncwarp();
         if (lane < (bn >> 6))
           tma_load_2d(xt + xb * x_bytes + lane * kABytes, &maps.x, &st->x_full[xb], n0 + lane * 64, m0);
-        if (++xb == 2) { xb = 0; x_phase ^= 1; }
-        for (int c = 0; c < nchunks; ++c) {
+        if (++xb == p.nxbuf) { xb = 0; x_phase ^= 1; }
+        for (int c = 0; c < nchunks && !onehot; ++c) {
           lv_wait(&st->empty[stage], phase ^ 1, spin);
           if (lane == 0) mbar_arrive_expect_tx(&st->full[stage], stage_tx);
           __syncwarp();
@@ -233,7 +248,7 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
         wfirst = false;
         umma_commit(&st->x_empty[xb]);
         umma_commit(&st->tmem_full[buf]);
-        if (++xb == 2) { xb = 0; x_phase ^= 1; }
+        if (++xb == p.nxbuf) { xb = 0; x_phase ^= 1; }
         if (++buf == p.nbuf) { buf = 0; buf_phase ^= 1; }
       }
       umma_commit(&st->w_full);
@@ -349,6 +364,67 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
       }
     }
   } else {
+    if (onehot) {
+      // ================= generator: the one-hot dz boxes, one row per thread =================
+      const int gw = warp - 10;
+      const uint32_t rr = static_cast<uint32_t>(gw * 32 + lane);     // row of the 128-point box
+      const float S = p.oh_scale ? *p.oh_scale : 1.f;
+      const float oneg = p.oh_act == PCADV_ACT_LEAKY ? p.oh_slope : 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      // (idx, val, dy) of the NEXT tile are requested before this tile's boxes are written
+      int n_hot = -1;
+      float n_val = 0.f, n_dy = 0.f;
+      auto fetch = [&](int64_t tt) {
+        const int64_t r = tt * kTileM + rr;
+        n_hot = -1; n_val = 0.f; n_dy = 0.f;
+        if (tt < p.tiles_m && r < p.rows) {
+          n_hot = __ldg(p.oh_idx + r);
+          n_dy = __ldg(p.oh_dy + r);
+          if (p.oh_act != PCADV_ACT_NONE) n_val = __ldg(p.oh_val + r);
+        }
+      };
+      fetch(t_first);
+      for (int64_t t = t_first; t < p.tiles_m; t += t_step) {
+        const int hot = n_hot;
+        const float d = p.oh_act == PCADV_ACT_NONE ? 1.f : (n_val > 0.f ? 1.f : oneg);
+        const float v = hot >= 0 ? n_dy * d * S : 0.f;
+        fetch(t + t_step);
+        if (slice == 0 && hot >= 0 && hot < nchunks * 64) atomicAdd(&st->hist[hot], v);
+        const uint32_t pk = kOut == PCADV_F16 ? pack_f16x2_sat(v, v) : pack_bf16x2(v, v);
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&st->empty[stage], phase ^ 1);
+          const uint32_t row_a = smem_u32(stages + stage * p.stage_bytes) + rr * 128;
+          const int hc = (hot >= c * 64 && hot < c * 64 + 64) ? hot - c * 64 : -1;   // hot channel inside this chunk
+#pragma unroll
+          for (uint32_t ph = 0; ph < 8; ++ph) {
+            const uint32_t lg = ph ^ (rr & 7);                       // logical 16-byte group at this position
+            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+            if (hc >= 0 && static_cast<uint32_t>(hc >> 3) == lg) {
+              const uint32_t e = static_cast<uint32_t>(hc & 7);
+              const uint32_t word = (e & 1) ? (pk & 0xffff0000u) : (pk & 0x0000ffffu);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (static_cast<uint32_t>(q) == (e >> 1)) w4[q] = word;
+            }
+            lv_sts128(row_a + (ph << 4), w4[0], w4[1], w4[2], w4[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st->full[stage]);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+      // bias gradient: the CTA's histogram, once all four generator warps are through
+      named_barrier_sync(3, 128);
+      if (slice == 0 && p.dbias[0] != nullptr) {
+        const float sc = p.scale ? *p.scale : 1.f;
+        for (int c = gw * 32 + lane; c < p.seg_k[0]; c += 128) {
+          const float h = st->hist[c];
+          if (h != 0.f) atomicAdd(p.dbias[0] + c, h * sc);
+        }
+      }
+    }
     // ================= column sums of the dz boxes in flight =================
     if (sums) {
       const int cw = warp - 10;                       // row quarter of the 128-point box
@@ -430,8 +506,9 @@ tc_level_kernel(const __grid_constant__ LvMaps maps, const LvParams p) {
   }
 }
 
-static size_t lv_smem_bytes(int nstages, int stage_bytes, int bn, int epi_warps, int nslabs, int wres_bytes = 0) {
-  return 1024 + static_cast<size_t>(nstages) * stage_bytes + wres_bytes + 2 * static_cast<size_t>(bn) * 256 +
+static size_t lv_smem_bytes(int nstages, int stage_bytes, int bn, int epi_warps, int nslabs, int wres_bytes = 0,
+                            int nxbuf = 2) {
+  return 1024 + static_cast<size_t>(nstages) * stage_bytes + wres_bytes + nxbuf * static_cast<size_t>(bn) * 256 +
          static_cast<size_t>(epi_warps) * nslabs * kLvSlabBytes + sizeof(LvTail) + 16;
 }
 
@@ -448,11 +525,16 @@ int tc_backlevel(const pcadv_backlevel_args& a, cudaStream_t s) {
   p.rows = a.rows; p.n = a.n;
   p.tiles_m = (a.rows + kTileM - 1) / kTileM;
   int nch = 0, ktot = 0, nsum = 0;
+  const bool onehot = a.onehot_idx != nullptr;
+  if (onehot && (a.num_seg != 1 || !a.onehot_dy || (a.onehot_act != PCADV_ACT_NONE && !a.onehot_val) ||
+                 a.seg[0].k > kLvOneHotMax))
+    return -1;
   for (int i = 0; i < a.num_seg; ++i) {
     const pcadv_seg& sg = a.seg[i];
-    if (sg.dtype != dt || sg.k % 64 != 0 || !tma_compatible(sg.ptr, dt, sg.ld)) return -1;
+    if (sg.dtype != dt || sg.k % 64 != 0 || (!onehot && !tma_compatible(sg.ptr, dt, sg.ld))) return -1;
     if (nch + sg.k / 64 > kLvMaxChunks) return -1;
-    const bool want_sum = a.dbias[i] != nullptr || a.dgroup[i] != nullptr;
+    const bool want_sum = !onehot && (a.dbias[i] != nullptr || a.dgroup[i] != nullptr);
+    if (onehot && a.dgroup[i]) return -1;
     for (int k0 = 0; k0 < sg.k; k0 += 64, ++nch) {
       p.chunk_seg[nch] = i; p.chunk_k0[nch] = k0; p.chunk_kg[nch] = ktot + k0;
       p.chunk_sum[nch] = want_sum ? nsum++ : -1;
@@ -460,7 +542,8 @@ int tc_backlevel(const pcadv_backlevel_args& a, cudaStream_t s) {
     p.seg_k[i] = sg.k;
     p.dw[i] = a.dw[i]; p.ld_dw[i] = a.ld_dw[i]; p.dbias[i] = a.dbias[i]; p.dgroup[i] = a.dgroup[i];
     if (a.dgroup[i] && (a.rows_per_group <= 0 || a.rows_per_group % kTileM != 0)) return -1;
-    if (int rc = encode_tmap_2d(&maps.seg[i], sg.ptr, dt, a.rows, sg.k, sg.ld, kBlockK, kTileM)) return rc;
+    if (!onehot)
+      if (int rc = encode_tmap_2d(&maps.seg[i], sg.ptr, dt, a.rows, sg.k, sg.ld, kBlockK, kTileM)) return rc;
     ktot += sg.k;
   }
   if (nsum > kLvMaxSum) return -1;
@@ -493,15 +576,25 @@ int tc_backlevel(const pcadv_backlevel_args& a, cudaStream_t s) {
   size_t smem = 0;
   // pick the layout with the most dz bytes in flight (the ring's turnaround -- load latency plus two
   // barrier wake-ups, ~2 us -- bounds the pipeline at ring bytes / turnaround); ties go to resident weights
-  for (int mode = want_wres ? 0 : 1; mode < 2; ++mode) {
+  if (onehot) want_wres = 1;
+  // narrow levels (few chunks per row tile) are bound by round trips per tile, so as many whole tiles as
+  // possible are kept in flight: score = min(dz tiles in the ring, x tiles buffered), then the ring depth
+  int best_score = -1;
+  for (int mode = want_wres ? 0 : 1; mode < (onehot ? 1 : 2); ++mode) {
     const int wres_bytes = mode == 0 ? nch * bn * 128 : 0;
     const int stage_bytes = kABytes + (mode == 0 ? 0 : bn * 128);
     for (int nslabs = 2; nslabs >= 1; --nslabs) {
-      int cand = kLvMaxStages;
-      while (cand >= 2 && lv_smem_bytes(cand, stage_bytes, bn, p.epi_warps, nslabs, wres_bytes) > static_cast<size_t>(kLvSmemMax)) cand -= 2;
-      if (cand >= 2 && cand > nst) {
-        nst = cand; p.nslabs = nslabs; p.wres = mode == 0 ? 1 : 0; p.stage_bytes = stage_bytes;
-        smem = lv_smem_bytes(cand, stage_bytes, bn, p.epi_warps, nslabs, wres_bytes);
+      for (int nx = 2; nx <= kLvMaxXBuf; ++nx) {
+        int cand = kLvMaxStages;
+        while (cand >= 2 && lv_smem_bytes(cand, stage_bytes, bn, p.epi_warps, nslabs, wres_bytes, nx) > static_cast<size_t>(kLvSmemMax)) cand -= 2;
+        if (cand < 2) continue;
+        const int tiles16 = cand * 16 / nch;                       // dz tiles in the ring, in 1/16
+        const int score = (tiles16 < nx * 16 ? tiles16 : nx * 16) * 64 + cand;
+        if (score > best_score) {
+          best_score = score;
+          nst = cand; p.nslabs = nslabs; p.nxbuf = nx; p.wres = mode == 0 ? 1 : 0; p.stage_bytes = stage_bytes;
+          smem = lv_smem_bytes(cand, stage_bytes, bn, p.epi_warps, nslabs, wres_bytes, nx);
+        }
       }
     }
   }
@@ -522,6 +615,11 @@ int tc_backlevel(const pcadv_backlevel_args& a, cudaStream_t s) {
   p.mask_neg = a.mask_act == PCADV_ACT_LEAKY ? a.mask_slope : 0.f;
   p.rows_per_group = a.rows_per_group;
   p.scale = a.scale;
+  if (onehot) {
+    if (!p.wres || (nch & 1)) return -1;
+    p.oh_dy = a.onehot_dy; p.oh_val = a.onehot_val; p.oh_idx = a.onehot_idx;
+    p.oh_act = a.onehot_act; p.oh_slope = a.onehot_slope; p.oh_scale = a.onehot_scale;
+  }
   p.vec_red = 1;
   if (const char* e = getenv("PCADV_LEVEL_DBG")) p.dbg = atoi(e);
   for (int i = 0; i < a.num_seg; ++i)
@@ -549,7 +647,8 @@ extern "C" int pcadv_backlevel(const pcadv_backlevel_args* a, void* stream) {
   PCADV_CHECK_ARG(a->rows >= 0 && a->n > 0, "pcadv_backlevel: bad shape rows=%lld n=%d", (long long)a->rows, a->n);
   PCADV_CHECK_ARG(a->num_seg >= 1 && a->num_seg <= PCADV_MAX_SEG, "pcadv_backlevel: num_seg=%d", a->num_seg);
   for (int i = 0; i < a->num_seg; ++i)
-    PCADV_CHECK_ARG(a->seg[i].ptr != nullptr && a->seg[i].k > 0, "pcadv_backlevel: bad segment %d", i);
+    PCADV_CHECK_ARG((a->seg[i].ptr != nullptr || a->onehot_idx != nullptr) && a->seg[i].k > 0,
+                    "pcadv_backlevel: bad segment %d", i);
   PCADV_CHECK_ARG(a->w && a->x && a->dz_out, "pcadv_backlevel: w, x and dz_out are required");
   PCADV_CHECK_ARG(a->mask_act == PCADV_ACT_NONE || a->mask_bits != nullptr,
                   "pcadv_backlevel: an activation mask needs mask_bits");

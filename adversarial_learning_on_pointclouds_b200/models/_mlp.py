@@ -5,6 +5,8 @@ per-cloud T-Net transform, and the orthogonality regulariser.
 Tensors that cross a Function boundary are fp32; inside, activations live in the
 precision mode's storage dtype and gradients carry a dynamic power-of-two scale.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -13,6 +15,13 @@ from ..ops import ACT_NONE, ENGINE_SIMT
 from ._chain import (Layer, ZeroPool, chain_forward, chain_backward, compute_weight, prepare_dz,
                      layer_wgrad, dgrad_weight)
 
+
+# Backward of "layer + activation + max over channels" through pcadv_backlevel's one-hot mode instead of the
+# two gather kernels: 0.30 -> 0.22 ms per 2^20 rows back to back (tools/level_ab.py), but the cfg5 step gets
+# SLOWER with it (15.58 -> 15.76 ms same box): the discriminator phase shares the GPU with the generator's
+# backward, where the gather kernels' small CTAs fill SMs as they free up and a 148-CTA persistent kernel
+# with a static row partition waits for whole SMs.  Off by default; PCADV_ONEHOT_LEVEL=1 enables it.
+_ONEHOT_LEVEL = os.environ.get("PCADV_ONEHOT_LEVEL", "0") == "1"
 
 # Tests set this to a list: every PointMLPFunction.forward appends the activations it saved (the
 # branch decisions of the pass) -- tests/parity.py builds the oracle's ``branch`` dict from it.
@@ -275,14 +284,29 @@ class PointMLPFunction(torch.autograd.Function):
                 # of a dense one-hot dz and two GEMMs over it
                 n, k_true = L.w.shape
                 dy = d_out.reshape(-1)
-                if need_w[-1] or need_b[-1]:
+                lb = len(body) - 1
+                if need_w[-1] and need_b[-1] and prec.scaled and n % 64 == 0 and n <= 256 and \
+                        _ONEHOT_LEVEL and ops.backlevel_eligible(prec, [n], src, ybits[lb]):
+                    # one pass over the pooled layer's input: its weight / bias gradient and the dz of the
+                    # layer below, the one-hot dz built inside the kernel (pcadv_backlevel, one-hot mode)
+                    P_ = body[-1]
+                    dw = pool.take(n, src.shape[1])
+                    db = pool.take(n)
+                    wt = dgrad_weight(prec, [L.w], src.shape[1], [n])
+                    dz_last = ops.backlevel(None, wt, src, mask_bits=ybits[lb], mask_act=P_.act,
+                                            mask_slope=P_.slope, dws=[dw], dbiases=[db], scale=inv,
+                                            onehot=(dy.contiguous().float(), red_val.reshape(-1), red_idx.reshape(-1),
+                                                    n, L.act, L.slope, S))
+                    grads[-1] = (dw[:, :k_true], db)
+                elif need_w[-1] or need_b[-1]:
                     dw = pool.take(n, src.shape[1]) if need_w[-1] else None
                     db = pool.take(n) if need_b[-1] else None
                     ops.rowmax_wgrad(dy, red_val, red_idx, src, n, act=L.act, slope=L.slope, dw=dw, dbias=db)
                     grads[-1] = (dw[:, :k_true] if dw is not None else None, db)
-                P_ = body[-1]
-                w_pad = compute_weight(prec, L.w, [src.shape[1]], n)
-                dz_last = ops.rowmax_dgrad(dy, red_val, red_idx, w_pad, src, act=L.act, slope=L.slope,
+                if dz_last is None:
+                    P_ = body[-1]
+                    w_pad = compute_weight(prec, L.w, [src.shape[1]], n)
+                    dz_last = ops.rowmax_dgrad(dy, red_val, red_idx, w_pad, src, act=L.act, slope=L.slope,
                                            scale=S, prev_act=P_.act, prev_slope=P_.slope,
                                            out_dtype=prec.act_dtype)
             elif spec.reduce == "channels":

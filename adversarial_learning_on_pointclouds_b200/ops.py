@@ -357,21 +357,33 @@ def backlevel_eligible(prec, ks, x, mask_bits, rows_per_group=0, want_group=Fals
 
 
 def backlevel(segs, w, x, *, mask_bits=None, mask_act=ACT_RELU, mask_slope=0.0, dws=None, dbiases=None,
-              dgroups=None, rows_per_group=0, scale=None, out=None):
+              dgroups=None, rows_per_group=0, scale=None, out=None, onehot=None):
     """See ``pcadv_backlevel``: dz_out = act'(x) * ([segs] @ w^T) together with the weight gradients
     ``dws[i] [k_i, n] += scale * segs[i]^T @ x``, ``dbiases[i] [k_i] += scale * colsum(segs[i])`` and the
     per-cloud column sums ``dgroups[i] [rows / rows_per_group, k_i]`` in one pass over ``segs``.
-    Returns dz_out ([rows, n], the dtype of x)."""
+    ``onehot`` = (dy [rows] fp32, val [rows] fp32, idx [rows] int32, n_pool, act, slope, scale | None): the single
+    segment is the gradient of a max over ``n_pool`` channels, generated inside the kernel (``segs`` is
+    ignored).  Returns dz_out ([rows, n], the dtype of x)."""
     a = _lib.BackLevelArgs()
     rows, n = x.shape
-    a.rows, a.n, a.num_seg = rows, n, len(segs)
-    ktot = 0
-    for i, s in enumerate(segs):
-        if s.shape[0] != rows or s.dtype != x.dtype:
-            raise ValueError("segment %d: expected [%d, k] %s" % (i, rows, x.dtype))
-        p, ld, dt = _mat(s)
-        a.seg[i].ptr, a.seg[i].ld, a.seg[i].k, a.seg[i].dtype = p, ld, s.shape[1], dt
-        ktot += s.shape[1]
+    if onehot is not None:
+        dy, val, idx, n_pool, oh_act, oh_slope, oh_scale = onehot
+        if idx.dtype != torch.int32 or not idx.is_contiguous() or idx.numel() != rows:
+            raise ValueError("onehot idx must be a contiguous int32 tensor with one entry per row")
+        widths = [int(n_pool)]
+        a.onehot_dy, a.onehot_val, a.onehot_idx = _f32(dy, rows), _f32(val, rows), _ptr(idx)
+        a.onehot_act, a.onehot_slope = oh_act, float(oh_slope)
+        a.onehot_scale = _f32(oh_scale) if oh_scale is not None else None
+        a.seg[0].ptr, a.seg[0].ld, a.seg[0].k, a.seg[0].dtype = None, int(n_pool), int(n_pool), _DT[x.dtype]
+    else:
+        widths = [s.shape[1] for s in segs]
+        for i, s in enumerate(segs):
+            if s.shape[0] != rows or s.dtype != x.dtype:
+                raise ValueError("segment %d: expected [%d, k] %s" % (i, rows, x.dtype))
+            p, ld, dt = _mat(s)
+            a.seg[i].ptr, a.seg[i].ld, a.seg[i].k, a.seg[i].dtype = p, ld, s.shape[1], dt
+    a.rows, a.n, a.num_seg = rows, n, len(widths)
+    ktot = sum(widths)
     if tuple(w.shape) != (n, ktot) or w.dtype != x.dtype:
         raise ValueError("weight %s does not match n=%d, ktot=%d" % (tuple(w.shape), n, ktot))
     a.w, a.ldw, _ = _mat(w)
@@ -381,25 +393,26 @@ def backlevel(segs, w, x, *, mask_bits=None, mask_act=ACT_RELU, mask_slope=0.0, 
         a.mask_act, a.mask_slope = mask_act, float(mask_slope)
     dz = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
     a.dz_out, a.ld_out, _ = _mat(dz)
-    for i, s in enumerate(segs):
+    for i, k in enumerate(widths):
         dw = dws[i] if dws else None
         if dw is not None:
             p, ld, dt = _mat(dw)
-            if dt != F32 or dw.shape[0] < s.shape[1] or dw.shape[1] != n:
-                raise ValueError("dws[%d] must be fp32 [>=%d, %d], got %s" % (i, s.shape[1], n, tuple(dw.shape)))
+            if dt != F32 or dw.shape[0] < k or dw.shape[1] != n:
+                raise ValueError("dws[%d] must be fp32 [>=%d, %d], got %s" % (i, k, n, tuple(dw.shape)))
             a.dw[i], a.ld_dw[i] = p, ld
         db = dbiases[i] if dbiases else None
         if db is not None:
-            if db.numel() < s.shape[1]:
-                raise ValueError("dbiases[%d] needs %d elements" % (i, s.shape[1]))
+            if db.numel() < k:
+                raise ValueError("dbiases[%d] needs %d elements" % (i, k))
             a.dbias[i] = _f32(db)
         dgp = dgroups[i] if dgroups else None
         if dgp is not None:
-            a.dgroup[i] = _f32(dgp, (rows // rows_per_group) * s.shape[1])
+            a.dgroup[i] = _f32(dgp, (rows // rows_per_group) * k)
     a.rows_per_group = int(rows_per_group)
     a.scale = _f32(scale) if scale is not None else None
     if rows > 0:
-        _call("backlevel:k%d:n%d" % (ktot, n), _lib.lib().pcadv_backlevel, C.byref(a), _stream(), rows=rows)
+        _call("backlevel:k%d:n%d%s" % (ktot, n, ":onehot" if onehot is not None else ""), _lib.lib().pcadv_backlevel,
+              C.byref(a), _stream(), rows=rows)
     return dz
 
 

@@ -214,6 +214,18 @@ typedef struct pcadv_backlevel_args {
   float* dgroup[PCADV_MAX_SEG];   /* [rows / rows_per_group, k_i] or NULL */
   int64_t rows_per_group;
   const float* scale;         /* device scalar or NULL */
+  /* Optional (onehot_idx != NULL; num_seg == 1, seg[0].ptr == NULL, seg[0].k = pooled channels, a multiple
+   * of 64): segment 0 is not read from memory -- it is the gradient of a max over channels
+   * (models/discriminator.py:71), built in shared memory one element per row:
+   *   dz_0[r, c] = (c == onehot_idx[r]) ? onehot_dy[r] * act'(onehot_val[r]) * (*onehot_scale) : 0
+   * (rounded to the 16-bit dtype; the bias gradient sums the unrounded values).  This is pcadv_rowmax_wgrad +
+   * pcadv_rowmax_dgrad in one pass over the pooled layer's input x. */
+  const float* onehot_dy;     /* [rows] */
+  const float* onehot_val;    /* [rows] pooled post-activation value */
+  const int32_t* onehot_idx;  /* [rows] argmax channel */
+  int32_t onehot_act;
+  float onehot_slope;
+  const float* onehot_scale;  /* device scalar or NULL */
 } pcadv_backlevel_args;
 
 int pcadv_backlevel(const pcadv_backlevel_args* a, void* stream);

@@ -287,3 +287,45 @@ def test_tc_backlevel(dtype, rows, ks, n, rpg, act):
     # second call accumulates
     ops.backlevel(segs, w, x, mask_bits=bits, mask_act=act, mask_slope=0.2, dws=dws, dbiases=dbs, scale=sc)
     assert rel_err(dws[0], 0.5 * (segs[0].double().t() @ x.double())) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,n_pool,k,act", [(5000, 128, 64, ACT_RELU), (129, 128, 64, ACT_LEAKY),
+                                               (40000, 64, 128, ACT_NONE), (4133, 256, 64, ACT_RELU)])
+def test_tc_backlevel_onehot(dtype, rows, n_pool, k, act):
+    """The one-hot mode of pcadv_backlevel (backward of "layer + activation + max over channels",
+    models/discriminator.py:67-72) against the gather kernels it replaces and fp64 torch."""
+    g = torch.Generator().manual_seed(77)
+    dy = torch.randn(rows, generator=g).to(DEV)
+    val = (torch.rand(rows, generator=g) - 0.3).to(DEV)          # some pooled values <= 0
+    idx = torch.randint(0, n_pool, (rows,), generator=g, dtype=torch.int32).to(DEV)
+    y = _rand((rows, k), 61, dtype).relu()
+    w = _rand((n_pool, k), 62, dtype, 0.1)                         # the pooled layer's weight
+    wt = w.t().contiguous()
+    pos = (y.float() > 0).reshape(rows, k // 32, 32).long()
+    j = torch.arange(32, device=DEV)
+    words = (pos << ((j >> 1) + 16 * (j & 1))).sum(2)
+    bits = (words - ((words >> 31) << 32)).to(torch.int32).contiguous()
+    S = torch.tensor([8.0], device=DEV)
+    inv = torch.tensor([0.125], device=DEV)
+    dw = torch.zeros((n_pool, k), device=DEV)
+    db = torch.zeros((n_pool,), device=DEV)
+    dz = ops.backlevel(None, wt, y, mask_bits=bits, mask_act=ACT_RELU, dws=[dw], dbiases=[db], scale=inv,
+                       onehot=(dy, val, idx, n_pool, act, 0.2, S))
+    torch.cuda.synchronize()
+    d = torch.ones_like(val) if act == ACT_NONE else torch.where(val > 0, torch.ones_like(val),
+                                                                 torch.full_like(val, 0.2 if act == ACT_LEAKY else 0.0))
+    s = (dy * d).double()
+    onehot = torch.zeros((rows, n_pool), dtype=torch.float64, device=DEV)
+    onehot[torch.arange(rows, device=DEV), idx.long()] = s
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2               # s itself is rounded to 16 bits
+    assert rel_err(dw, onehot.t() @ y.double()) < tol
+    assert rel_err(db, onehot.sum(0)) < 1e-5                        # the bias sums the unrounded values
+    ref_dz = (onehot * 8.0) @ w.double() * (y > 0)
+    assert rel_err(dz, ref_dz) < tol
+    # the gather kernels it stands in for
+    dw2 = torch.zeros_like(dw)
+    db2 = torch.zeros_like(db)
+    ops.rowmax_wgrad(dy, val, idx, y, n_pool, act=act, slope=0.2, dw=dw2, dbias=db2)
+    dz2 = ops.rowmax_dgrad(dy, val, idx, w, y, act=act, slope=0.2, scale=S, prev_act=ACT_RELU, out_dtype=dtype)
+    assert rel_err(dw, dw2) < tol and rel_err(db, db2) < 1e-5 and rel_err(dz, dz2) < tol

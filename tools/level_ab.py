@@ -105,6 +105,11 @@ def main():
         def nw():
             dz = ops.rowmax_bwd(dy, val, idx, n, act=ACT_RELU, scale=s1, out_dtype=torch.float16)
             ops.backlevel([dz], wt, y, mask_bits=bt, dws=[dw], dbiases=[db], scale=s1)
+        def nw2():
+            ops.backlevel(None, wt, y, mask_bits=bt, dws=[dw], dbiases=[db], scale=s1,
+                          onehot=(dy, val, idx, n, ACT_RELU, 0.0, s1))
+        if os.environ.get("LEVEL_AB_ONEHOT", "1") != "0":
+            return "rowmax level n128 k64 (gather | one-hot in kernel)", o, nw2
         return "rowmax level n128 k64 (gather | one-hot)", o, nw
 
     cases = [("trunk levels 3,2,1 + fc1 wgrad", old, new), rowmax_case(P // 2), pair("fc4 level k64 n128", 64, 128, P),
