@@ -329,3 +329,34 @@ def test_tc_backlevel_onehot(dtype, rows, n_pool, k, act):
     ops.rowmax_wgrad(dy, val, idx, y, n_pool, act=act, slope=0.2, dw=dw2, dbias=db2)
     dz2 = ops.rowmax_dgrad(dy, val, idx, w, y, act=act, slope=0.2, scale=S, prev_act=ACT_RELU, out_dtype=dtype)
     assert rel_err(dw, dw2) < tol and rel_err(db, db2) < 1e-5 and rel_err(dz, dz2) < tol
+
+
+@pytest.mark.parametrize("rows", [129, 389, 1000, 4133])
+@pytest.mark.parametrize("ks,n", [([64], 128), ([128, 256], 64), ([128], 256)])
+def test_backlevel_does_not_overrun_caller_buffers(rows, ks, n):
+    """Guard words around dz_out, dW and dbias of pcadv_backlevel stay untouched for ragged row
+    counts (compute-sanitizer is closed on the pool: this is the bounds check)."""
+    dtype = torch.float16
+    segs = [_rand((rows, k), 70 + i, dtype) for i, k in enumerate(ks)]
+    w = _rand((n, sum(ks)), 80, dtype, 0.1)
+    x = _rand((rows, n), 81, dtype).relu()
+    bits = torch.full((rows, n // 32), -1, dtype=torch.int32, device=DEV)      # every sign bit set
+    guard = 256
+    raw16 = torch.full((rows * n + 2 * guard,), 3.5, dtype=dtype, device=DEV)
+    out = raw16[guard:guard + rows * n].view(rows, n)
+    sizes = [k * n for k in ks] + [ks[0]]
+    rawf = torch.full((sum(sizes) + 2 * guard,), 7.25, dtype=torch.float32, device=DEV)
+    off, dws = guard, []
+    for k in ks:
+        dws.append(rawf[off:off + k * n].view(k, n))
+        off += k * n
+    db = rawf[off:off + ks[0]]
+    for t in dws + [db]:
+        t.zero_()
+    ops.backlevel(segs, w, x, mask_bits=bits, dws=dws, dbiases=[db] + [None] * (len(ks) - 1), out=out)
+    torch.cuda.synchronize()
+    assert (raw16[:guard] == 3.5).all() and (raw16[guard + rows * n:] == 3.5).all()
+    assert (rawf[:guard] == 7.25).all() and (rawf[off + ks[0]:] == 7.25).all()
+    assert rel_err(out, torch.cat(segs, 1).double() @ w.double().t()) < 1e-3
+    assert rel_err(dws[-1], segs[-1].double().t() @ x.double()) < 1e-5
+    assert rel_err(db, segs[0].double().sum(0)) < 1e-5
