@@ -7,18 +7,23 @@
 // layer's MMA wants, so layer l + 1 multiplies straight out of shared memory and no intermediate
 // activation is read back from HBM (they are still written once: the backward needs them).
 //
-// 320 threads as in tc_rows.cu: warp 0 TMA producer (layer 0's A chunks and every layer's weight
+// 64 + 128 G threads, G = 2 or 3 epilogue groups (three where every accumulator is <= 128 columns wide:
+// TMEM then holds a third tile, and one layer of one tile being a single dependency chain of ~5 600
+// cycles, a third tile in flight is worth 19 % on the trunk and 26 % on the discriminator's chain).
+// As in tc_rows.cu: warp 0 TMA producer (layer 0's A chunks and every layer's weight
 // chunks, in the order the MMA thread consumes them), warp 1 MMA issuer, warps 2..9 two epilogue
 // halves.  Half h owns TMEM columns [256 h, 256 h + 256) and the shared-memory tile H[h]; the CTA's
 // tiles alternate between the halves, and for every (tile, layer) the MMA thread and the half
 // ping-pong on two barriers: acc_full[h] (MMA done -> epilogue) and in_ready[h] (H[h] holds the
 // layer's output and the accumulator is free -> next MMA).
+#include <stdlib.h>
 #include "tc_pipeline.cuh"
 
 namespace pcadv {
 namespace tc {
 
-constexpr int kChainThreads = 320;
+constexpr int kChainMaxGroups = 3;                // epilogue groups = tiles in flight
+__host__ __device__ constexpr int chain_threads(int groups) { return 64 + 128 * groups; }
 constexpr int kChainMaxLayers = 4;
 constexpr int kChainMaxStages = 6;
 constexpr int kChainSmemMax = 232448;
@@ -33,8 +38,8 @@ struct ChainMaps {
 struct ChainTail {
   uint64_t full[kChainMaxStages];
   uint64_t empty[kChainMaxStages];
-  uint64_t acc_full[2];
-  uint64_t in_ready[2];
+  uint64_t acc_full[kChainMaxGroups];
+  uint64_t in_ready[kChainMaxGroups];
   uint32_t tmem_base;
 };
 
@@ -56,6 +61,7 @@ struct ChainParams {
   float* out_f32;                             // last layer: fp32 rows [rows, n_f32] (contiguous) instead
   int n_f32;                                  //   of a 16-bit TMA-stored output (n_f32 <= 64 <= n[last])
   int serial;                                 // one tile in flight, both halves split its steps (wide chains)
+  int groups;                                 // epilogue groups of four warps = tiles in flight (2, or 3 when every n <= 128)
   int nstages, stage_bytes, h_bytes;
   int bf16;
   // debugging aid (pcadv_debug_chain_trace): clock64 stamps of CTA 0, [warp 0..9][slot 0..kTraceSlots)
@@ -72,9 +78,9 @@ constexpr int kTraceSlots = 256;
 
 struct ChainSmem {
   uint8_t* stages;
-  uint8_t* H;                                 // [2 halves][h_bytes]
+  uint8_t* H;                                 // [groups][h_bytes]
   float* bias;                                // [layers][256]
-  uint32_t* bits;                             // [8 warps][32 rows][8 words]
+  uint32_t* bits;                             // [4 * groups warps][32 rows][8 words]
   ChainTail* tail;
 };
 
@@ -82,15 +88,15 @@ __device__ __forceinline__ ChainSmem carve_chain(uint8_t* raw, const ChainParams
   ChainSmem L;
   L.stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   L.H = L.stages + p.nstages * p.stage_bytes;
-  L.bias = reinterpret_cast<float*>(L.H + 2 * p.h_bytes);
+  L.bias = reinterpret_cast<float*>(L.H + p.groups * p.h_bytes);
   L.bits = reinterpret_cast<uint32_t*>(L.bias + kChainMaxLayers * kMaxTileN);
-  L.tail = reinterpret_cast<ChainTail*>(L.bits + 8 * 32 * kChainBitsWords);
+  L.tail = reinterpret_cast<ChainTail*>(L.bits + 4 * p.groups * 32 * kChainBitsWords);
   return L;
 }
 
-static size_t chain_smem_bytes(int nstages, int stage_bytes, int h_bytes) {
-  return 1024 + static_cast<size_t>(nstages) * stage_bytes + 2 * static_cast<size_t>(h_bytes) +
-         kChainMaxLayers * kMaxTileN * 4 + 8 * 32 * kChainBitsWords * 4 + sizeof(ChainTail) + 16;
+static size_t chain_smem_bytes(int nstages, int stage_bytes, int h_bytes, int groups = 2) {
+  return 1024 + static_cast<size_t>(nstages) * stage_bytes + groups * static_cast<size_t>(h_bytes) +
+         kChainMaxLayers * kMaxTileN * 4 + 4 * groups * 32 * kChainBitsWords * 4 + sizeof(ChainTail) + 16;
 }
 
 __device__ __forceinline__ float4 c_lds128(uint32_t addr) {
@@ -123,16 +129,18 @@ __device__ __forceinline__ uint32_t c_gt0_mask(uint32_t packed) {
   return m;
 }
 
-template <bool kBf16>
-__global__ void __launch_bounds__(kChainThreads, 1)
+template <bool kBf16, int kG>
+__global__ void __launch_bounds__(chain_threads(kG), 1)
 tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  constexpr int kChainThreads = chain_threads(kG);
+  constexpr uint32_t kGroupCols = kG == 2 ? kMaxTileN : 128;   // TMEM columns of a group's accumulator
   extern __shared__ uint8_t smem_raw[];
   const ChainSmem L = carve_chain(smem_raw, p);
   ChainTail* st = L.tail;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int NL = p.num_layers;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  const bool tracing = kG == 2 && p.trace != nullptr && blockIdx.x == 0;   // the trace buffer has ten warps
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.x);
@@ -144,7 +152,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       mbar_init(&st->full[i], 1);
       mbar_init(&st->empty[i], 1);
     }
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kG; ++h) {
       mbar_init(&st->acc_full[h], 1);
       mbar_init(&st->in_ready[h], p.serial ? 8 : 4);
     }
@@ -164,7 +172,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   const int64_t my_tiles = p.tiles > blockIdx.x ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   // serial mode (chains with a 256-wide intermediate: one shared-memory tile only): one tile in
   // flight in accumulator / tile 0, and the two epilogue halves take alternate 64-column steps of it
-  const int tiles_in_flight = p.serial ? 1 : 2;
+  const int tiles_in_flight = p.serial ? 1 : kG;
 
   if (warp == 0) {
     // ================= TMA producer: same (pair, layer, half, chunk) order as the MMA thread =====
@@ -194,19 +202,24 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t ready_par[2] = {0, 0};                    // parity of the next in_ready wait per half
+      uint32_t ready_par[kChainMaxGroups] = {0, 0, 0};   // parity of the next in_ready wait per group
       for (int64_t i0 = 0; i0 < my_tiles; i0 += tiles_in_flight) {
         for (int l = 0; l < NL; ++l) {
           const int chunks = p.k[l] >> 6;
           for (int h = 0; h < tiles_in_flight && i0 + h < my_tiles; ++h) {
             // H[h] holds the previous layer's output (l > 0) and the accumulator has been drained
-            const int tslot = static_cast<int>(((i0 / tiles_in_flight) * NL + l) * 2 + h) * 3;
+            const int tslot = static_cast<int>(((i0 / tiles_in_flight) * NL + l) * kG + h) * 3;
             CHAIN_STAMP(tslot);
-            mbar_wait_backoff(&st->in_ready[h], ready_par[h] ^ 1);
+            uint32_t rp = ready_par[0];
+            if (h == 1) rp = ready_par[1];
+            else if (h == 2) rp = ready_par[2];
+            mbar_wait_backoff(&st->in_ready[h], rp ^ 1);
             CHAIN_STAMP(tslot + 1);
-            ready_par[h] ^= 1;
+            if (h == 0) ready_par[0] ^= 1;
+            else if (h == 1) ready_par[1] ^= 1;
+            else ready_par[2] ^= 1;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(h * kMaxTileN);
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(h) * kGroupCols;
             const uint32_t h_addr = smem_u32(L.H + h * p.h_bytes);
             for (int c = 0; c < chunks; ++c) {
               mbar_wait_backoff(&st->full[stage], phase);
@@ -236,7 +249,7 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const uint32_t bits_s = smem_u32(L.bits + ew * 32 * kChainBitsWords);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                            static_cast<uint32_t>(buf * kMaxTileN);
+                            static_cast<uint32_t>(buf) * kGroupCols;
     uint32_t full_par = 0;
     for (int64_t i = p.serial ? 0 : half; i < my_tiles; i += tiles_in_flight) {
       const int64_t tm = blockIdx.x + i * gridDim.x;
@@ -478,21 +491,36 @@ extern "C" int pcadv_chain(const pcadv_chain_args* a, void* stream) {
   // one tile at a time and let both epilogue halves split its steps
   p.serial = chain_smem_bytes(2, p.stage_bytes, p.h_bytes) > static_cast<size_t>(kChainSmemMax) ? 1 : 0;
   if (p.serial) p.h_bytes /= 2;                                 // carve_chain lays out 2 * h_bytes
+  p.groups = 2;
+  // A layer of a tile is one dependency chain (MMA -> wake -> epilogue -> wake -> next MMA, ~5 600 cycles,
+  // profiles/r01h_chain_trace_cta0.txt) and only whole tiles run side by side: with every accumulator
+  // <= 128 columns wide TMEM holds a third tile, and a third group of four epilogue warps takes it.
+  static int want_groups = -1;
+  if (want_groups < 0) { const char* e = getenv("PCADV_CHAIN_GROUPS"); want_groups = e ? atoi(e) : 3; }   // tuning aid
+  if (!p.serial && want_groups >= 3 && max_kn <= 128 &&
+      chain_smem_bytes(3, p.stage_bytes, p.h_bytes, 3) <= static_cast<size_t>(kChainSmemMax))
+    p.groups = 3;
+  // (a fourth group fits for the discriminator's 64-wide chain and measured slower: 0.176 against 0.156 ms)
   int nst = kChainMaxStages;
-  while (nst > 2 && chain_smem_bytes(nst, p.stage_bytes, p.h_bytes) > static_cast<size_t>(kChainSmemMax)) --nst;
+  while (nst > 2 && chain_smem_bytes(nst, p.stage_bytes, p.h_bytes, p.groups) > static_cast<size_t>(kChainSmemMax)) --nst;
   p.nstages = nst;
-  const size_t smem = chain_smem_bytes(nst, p.stage_bytes, p.h_bytes);
+  const size_t smem = chain_smem_bytes(nst, p.stage_bytes, p.h_bytes, p.groups);
   PCADV_CHECK_ARG(smem <= static_cast<size_t>(kChainSmemMax), "pcadv_chain: shared memory budget exceeded");
   static bool attr_done = false;
   if (!attr_done) {
-    PCADV_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
-    PCADV_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
+    PCADV_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
+    PCADV_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
+    PCADV_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
+    PCADV_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
     attr_done = true;
   }
   const int grid = static_cast<int>(p.tiles < num_sms() ? p.tiles : num_sms());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dt == PCADV_BF16) tc_chain_kernel<true><<<grid, kChainThreads, smem, s>>>(maps, p);
-  else tc_chain_kernel<false><<<grid, kChainThreads, smem, s>>>(maps, p);
+  if (p.groups == 3) {
+    if (dt == PCADV_BF16) tc_chain_kernel<true, 3><<<grid, chain_threads(3), smem, s>>>(maps, p);
+    else tc_chain_kernel<false, 3><<<grid, chain_threads(3), smem, s>>>(maps, p);
+  } else if (dt == PCADV_BF16) tc_chain_kernel<true, 2><<<grid, chain_threads(2), smem, s>>>(maps, p);
+  else tc_chain_kernel<false, 2><<<grid, chain_threads(2), smem, s>>>(maps, p);
   PCADV_LAUNCHED();
   return 0;
 }

@@ -76,7 +76,7 @@ def cases(P, N):
     lin("disc4max", [64], 128, rowmax=True, want_out=False)
 
     # chained narrow layers (pcadv_chain): the generator trunk conv2 -> conv4 and the head tail
-    def chain(name, k0, widths, last_f32=False):
+    def chain(name, k0, widths, last_f32=False, rowmax=False):
         x = r16((P, k0))
         layers, k = [], k0
         for i, n in enumerate(widths):
@@ -86,10 +86,13 @@ def cases(P, N):
         nb = P * 2 * k0 + sum(P * (4 * n if (last_f32 and i == len(widths) - 1) else 2 * n + n // 8)
                               for i, n in enumerate(widths))
         fl = 2.0 * P * sum(a * b for a, b in zip([k0] + widths[:-1], widths))
-        c[name] = (lambda: ops.chain(x, layers, last_f32=last_f32), nb, fl)
+        if rowmax:      # the last layer stores nothing but the 8-byte key
+            nb -= P * (2 * widths[-1] + widths[-1] // 8) - 8 * P
+        c[name] = (lambda: ops.chain(x, layers, last_f32=last_f32, rowmax=rowmax), nb, fl)
 
     chain("chain_trunk", 64, [128, 128, 128])
     chain("chain_tail", 256, [128, 50], last_f32=True)
+    chain("chain_disc", 64, [64, 64, 64, 128], rowmax=True)
 
     def wg(name, n, ks, dbias=True):
         dz = r16((P, n))
