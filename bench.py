@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
             self.stop_flag.wait(0.02)
 
     def summary(self):
-        sm, reasons, smax = [], set(), None
+        sm, watts, reasons, smax = [], [], set(), None
         for s in self.samples:
             if len(s) < 7:
                 continue
@@ -94,13 +94,18 @@ class ClockSampler(threading.Thread):
                 sm.append(float(s[0])); smax = float(s[1])
             except ValueError:
                 continue
+            try:
+                watts.append(float(s[2]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                 "sw_power_cap"), s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        watts.sort()
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), power_w=watts[len(watts) // 2] if watts else None)
 
 
 def synthetic_inputs(B, N, seed):

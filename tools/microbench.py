@@ -132,6 +132,8 @@ def cases(P, N):
                                          rows_per_group=N, scale=s1, out=out), nbytes, 4.0 * P * sum(ks) * n)
 
     lv("lv_fc4", [64], 128)
+    lv("lv_d", [64], 64)
+    lv("lv_d_nosum", [64], 64, nsum=0)
     lv("lv_fc3", [128], 256)
     lv("lv_fc2", [256], 256)
     lv("lv5", [256], 512, group=True, nsum=0)
