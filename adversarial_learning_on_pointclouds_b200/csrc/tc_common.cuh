@@ -38,6 +38,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// (A suspend-time hint on these waits as well -- the epilogue warps' -- changes neither the step time nor
+// the board power: 15.03 / 15.05 ms at 985-989 W without, 15.02 / 15.02 ms with, same box.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   while (!mbar_try_wait(addr, parity)) {
