@@ -438,15 +438,17 @@ void launch_apply16(const pcadv_maxbwd_args& a, unsigned blocks, cudaStream_t s)
 
 // dW / dbias, 16-bit x rows gathered with 16-byte loads: one CTA per channel c, 8 warps stride
 // over the clouds (four clouds per trip), no atomics.
-template <bool kBf16>
+// kV = 16-byte vector columns per lane (k <= 256 kV: 1 / 2 / 4), so that k = 512 keeps 16 accumulators,
+// not 32, and three CTAs stay resident with eight gathers in flight per lane
+template <bool kBf16, int kV>
 __global__ void __launch_bounds__(256) maxbwd_dw16_kernel(const pcadv_maxbwd_args a) {
   __shared__ float red[8][1024];
   __shared__ float bred[8];
   const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = a.k >> 3;
-  float acc[kMaxVec][8];
+  float acc[kV][8];
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j)
+  for (int j = 0; j < kV; ++j)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
   float bsum = 0.f;
@@ -477,22 +479,31 @@ __global__ void __launch_bounds__(256) maxbwd_dw16_kernel(const pcadv_maxbwd_arg
     for (int u = 0; u < 4; ++u) { dz[u] = ndz[u]; r[u] = nr[u]; bsum += dz[u]; }
     if (g0 + 32 < a.groups) fetch(g0 + 32);
     if (a.dw) {
+      // the row gathers of two vector columns (eight 16-byte loads per lane) are issued before the first
+      // FMA: the kernel is latency-bound (22 cycles per issued instruction at 31 % issue utilisation)
 #pragma unroll
-      for (int j = 0; j < kMaxVec; ++j) {
-        const int v = lane + 32 * j;
-        if (v < nvec) {
-          uint4 x[4];
+      for (int j0 = 0; j0 < kV; j0 += 2) {
+        uint4 x[2][4];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int v = lane + 32 * (j0 + jj);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            x[u] = dz[u] != 0.f ? __ldg(xbase + r[u] * ldx4 + v) : make_uint4(0u, 0u, 0u, 0u);
+            x[jj][u] = (j0 + jj < kV && v < nvec && dz[u] != 0.f) ? __ldg(xbase + r[u] * ldx4 + v)
+                                                                      : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) fma8<kBf16>(x[u], dz[u], acc[j]);
+        for (int jj = 0; jj < 2; ++jj) {
+          if (j0 + jj < kV && lane + 32 * (j0 + jj) < nvec) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fma8<kBf16>(x[jj][u], dz[u], acc[j0 + jj]);
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j) {
+  for (int j = 0; j < kV; ++j) {
     const int v = lane + 32 * j;
     if (v < nvec) {
 #pragma unroll
@@ -875,8 +886,16 @@ extern "C" int pcadv_maxpool_bwd(const pcadv_maxbwd_args* a, void* stream) {
     PCADV_CHECK_ARG(!a->dw || a->x, "pcadv_maxpool_bwd: dw needs x");
     const bool x16 = a->x && a->x_dtype != PCADV_F32 && a->k % 8 == 0 && a->k <= 8 * 32 * kMaxVec &&
                      a->ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0;
-    if (x16 && a->x_dtype == PCADV_BF16) maxbwd_dw16_kernel<true><<<a->n, 256, 0, s>>>(*a);
-    else if (x16) maxbwd_dw16_kernel<false><<<a->n, 256, 0, s>>>(*a);
+    const int kv16 = (a->k / 8 + 31) / 32;               // 16-byte vector columns per lane
+    if (x16 && a->x_dtype == PCADV_BF16) {
+      if (kv16 <= 1) maxbwd_dw16_kernel<true, 1><<<a->n, 256, 0, s>>>(*a);
+      else if (kv16 == 2) maxbwd_dw16_kernel<true, 2><<<a->n, 256, 0, s>>>(*a);
+      else maxbwd_dw16_kernel<true, 4><<<a->n, 256, 0, s>>>(*a);
+    } else if (x16) {
+      if (kv16 <= 1) maxbwd_dw16_kernel<false, 1><<<a->n, 256, 0, s>>>(*a);
+      else if (kv16 == 2) maxbwd_dw16_kernel<false, 2><<<a->n, 256, 0, s>>>(*a);
+      else maxbwd_dw16_kernel<false, 4><<<a->n, 256, 0, s>>>(*a);
+    }
     else if (fast) maxbwd_dw_fast_kernel<<<a->n, 256, 0, s>>>(*a);
     else maxbwd_dw_kernel<<<a->n, 128, 0, s>>>(*a);
     PCADV_LAUNCHED();
