@@ -607,6 +607,9 @@ def run_cuda_adv(args):
                     "peak_sustained": peaks.get("bf16_sustained"),
                     "frac_of_sustained": achieved / peaks["bf16_sustained"],
                     "launch_ms": per_launch_s * 1e3, "share_of_step": tot_ms / ms_eager,
+                    # the same launches against the TIMED (graph-replayed) step -- the share an ncu launch
+                    # list of the step shows (its kernels are serialised, like the graph's)
+                    "share_of_timed_step": (tot_ms / args.steps) / ms,
                     "timing": "CUDA events around the launch on the launching stream, in an eager "
                               "pass of the same step (%d steps, %.2f ms/step eager)" % (args.steps,
                                                                                        ms_eager / args.steps)}
