@@ -13,12 +13,21 @@
 // dz channels stay resident in TMEM for the CTA's whole row range (K / 128 tiles of bn columns);
 // the dgrad accumulator takes the remaining columns (double-buffered where they fit).  Wide levels
 // are split over the output channels: CTA i owns slice i % slices of bn columns and walks the row
-// tiles i / slices, i / slices + grid / slices, ... -- the CTAs of one row tile run side by side, so
-// the second read of the dz tile is an L2 hit.
+// tiles i / slices, i / slices + grid / slices, ... -- the CTAs of one row tile run side by side, but
+// nothing keeps them in step and measured the second slice's read of a dz tile misses L2 more often
+// than not (K = 768 -> 128: 3.2 GB of DRAM reads for 1.9 GB algorithmic), which is why the models keep
+// the wide levels on separate dgrad / wgrad launches.  Narrow levels (K <= 128, what the
+// models use) keep up to four row tiles of dz and of x in flight: a tile there is 36-82 KB and its
+// round trips, not its bytes, set the pace.
+//
+// One-hot mode: the single dz segment is the gradient of a max over channels (one non-zero per row)
+// and is written into the ring by the four warps that otherwise take the column sums, straight from
+// (dy, pooled value, argmax) -- the backward of the discriminators' last layer without gather kernels.
 //
 // 448 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = dgrad epilogue (two halves,
 // as in tc_rows.cu) and, at the end, the drain of the weight-gradient accumulators (vector fp32 RED),
-// warps 10..13 = column sums of the dz boxes in flight (bias gradients, per-cloud sums).
+// warps 10..13 = column sums of the dz boxes in flight (bias gradients, per-cloud sums) or, in the
+// one-hot mode, the generator of those boxes.
 #include <stdlib.h>
 #include "tc_pipeline.cuh"
 
