@@ -67,3 +67,36 @@ def test_disc_onehot_level_agrees_with_gather_kernels(N):
     worst = max([rel_err(dx1, dx0)] + [rel_err(g1[k], g0[k]) for k in g0])
     print("PointwiseDiscNet", N, "worst difference one-hot level against gather kernels: %.2e" % worst)
     assert worst < 2e-3, worst
+
+
+_PAIR_SNIPPET = r"""
+import torch
+from adversarial_learning_on_pointclouds_b200 import ops
+from adversarial_learning_on_pointclouds_b200.ops import ACT_RELU, ENGINE_TC
+torch.manual_seed(0)
+worst = 0.0
+for rows, ks, n in [(3000, [64, 128, 128, 128, 512], 256), (777, [512, 256], 128), (4133, [256], 512), (129, [128], 64)]:
+    segs = [torch.randn(rows, k, device="cuda").half() for k in ks]
+    w = (torch.randn(n, sum(ks), device="cuda") * 0.1).half()
+    b = torch.randn(n, device="cuda")
+    out, _, _ = ops.linear(segs, w, bias=b, act=ACT_RELU, out_dtype=torch.float16, engine=ENGINE_TC)
+    ref = torch.relu(torch.cat(segs, 1).double() @ w.double().t() + b.double())
+    worst = max(worst, ((out.double() - ref).norm() / ref.norm()).item())
+print("PAIR_WORST %.3e" % worst)
+"""
+
+
+def test_rows_kernel_cta_pairs_with_multicast_weights():
+    """The optional CTA-pair mode of the rows kernel (clusters of two, TMA-multicast weight tiles; the
+    environment switch is read once per process, hence the child process), incl. an odd number of row
+    tiles (the pair's phantom tail tile)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PCADV_ROWS_PAIR="2", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", _PAIR_SNIPPET], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("PAIR_WORST")[-1])
+    print("rows kernel on CTA pairs: worst relative error %.2e" % worst)
+    assert worst < 1e-3
