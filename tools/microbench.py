@@ -112,6 +112,8 @@ def cases(P, N):
     c["wg_fc1_g"] = (lambda: ops.wgrad(dzg, segg, dw=dwg[:, :960], dgroup_bias=dcb, rows_per_group=N,
                                        scale=s2[1:2], engine=ENGINE_TC), P * 2 * (256 + 960), 2.0 * P * 256 * 960)
     wg("wg_conv5", 512, [128])
+    wg("wg_conv5_swapped", 128, [512], dbias=False)      # x4 as the M side, dz5 as eight N boxes: every byte once
+    wg("wg_fc2_swapped", 256, [256], dbias=False)
     wg("wg_fc2", 256, [256])
     wg("wg_conv3", 128, [128])
     wg("wg_d2", 64, [64])
