@@ -60,6 +60,7 @@ def cases(P, N):
     lin("fc2_bits", [256], 256, bits=True)
     lin("dz_fc1_mb", [256], 256, maskbits=True, bias=False)
     lin("dz4_mb", [512, 256], 128, maskbits=True, bias=False)
+    lin("dz5_mb", [256], 512, maskbits=True, bias=False)
     lin("d2_bits", [64], 64, bits=True)
     lin("conv6max", [512], 2048, colmax=True, want_out=False)
     lin("fc1", [64, 128, 128, 128, 512], 256, gb=True, bias=False)
