@@ -33,6 +33,7 @@ class LinearArgs(C.Structure):
         ("colmax_key", C.c_void_p), ("rowmax_key", C.c_void_p),
         ("bits_out", C.c_void_p), ("ld_bits_out", C.c_int64),
         ("mask_bits", C.c_void_p), ("ld_mask_bits", C.c_int64),
+        ("seg0_group_sum", C.c_void_p),
     ]
 
 

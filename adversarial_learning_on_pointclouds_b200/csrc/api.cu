@@ -56,6 +56,8 @@ extern "C" int pcadv_linear(const pcadv_linear_args* a, void* stream) {
   PCADV_CHECK_ARG(!(a->group_bias || a->colmax_key) || a->rows_per_group > 0,
                   "pcadv_linear: rows_per_group required with group_bias / colmax_key");
   PCADV_CHECK_ARG(a->out || a->colmax_key || a->rowmax_key, "pcadv_linear: no output requested");
+  PCADV_CHECK_ARG(!a->seg0_group_sum || (a->engine == PCADV_ENGINE_TC && a->rows_per_group > 0),
+                  "pcadv_linear: seg0_group_sum needs the tensor-core engine and rows_per_group");
   PCADV_CHECK_ARG(!a->out || valid_fdtype(a->out_dtype), "pcadv_linear: bad out dtype");
   if (a->rows == 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

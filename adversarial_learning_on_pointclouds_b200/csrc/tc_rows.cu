@@ -44,6 +44,7 @@ struct RowsParams {
   int64_t tiles_m, tiles_n;
   uint32_t idesc;
   int nstages, nslabs, stage_bytes;
+  float* group_sum;       // lean dgrad variant with column-sum warps: per-cloud column sums of segment 0
   int pair;               // CTA pairs (cluster of 2): each CTA fetches half of a weight tile and multicasts it to both
   int epi_halves;         // lean kernel: 2 = two epilogue halves (one TMEM buffer each), 1 = one half drains both
   // epilogue
@@ -123,7 +124,7 @@ __device__ __forceinline__ uint32_t rows_setup(const TensorMaps& maps, const Row
     for (int i = 0; i < kRowsMaxStages; ++i) {
       mbar_init(&st->full[i], 1);
       // pairs: a stage is refilled (partly by the peer's multicast) once BOTH CTAs have consumed it
-      mbar_init(&st->empty[i], p.pair ? 2 : 1);
+      mbar_init(&st->empty[i], (p.pair ? 2 : 1) + (p.group_sum ? 4 : 0));   // + the four column-sum warps
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&st->tmem_full[i], 1);
@@ -159,6 +160,15 @@ __device__ __forceinline__ RowsWork rows_work(const RowsParams& p) {
     w.first = blockIdx.x >> 1;
     w.stride = gridDim.x >> 1;
     w.count = ((p.tiles_m + 1) >> 1) * p.tiles_n;
+  } else if (p.group_sum) {
+    // column-sum variant: every CTA takes a CONTIGUOUS range of items, so that consecutive row tiles of a CTA lie
+    // in the same cloud and the per-cloud sums are reduced and flushed once per cloud, not once per tile
+    const int64_t total = p.tiles_m * p.tiles_n;
+    const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+    w.rank = 0;
+    w.first = blockIdx.x * per;
+    w.stride = 1;
+    w.count = w.first + per < total ? w.first + per : total;
   } else {
     w.rank = 0;
     w.first = blockIdx.x;
@@ -278,8 +288,108 @@ constexpr int kAddNone = 0, kAddBias = 1, kAddBiasGroup = 2;
 // addend / row-max / output scale.  kAdd: what is added to the accumulator (nothing -- dgrad;
 // bias -- forward layers; bias + per-cloud bias -- fc1).  kMaskBits: multiply by act'(.) read from
 // the forward layer's sign-bit map (dgrad).  Emits the sign-bit map of its own output on request.
-template <int kAct, int kOut, int kAdd, bool kMaskBits, bool kRowMax = false>
-__global__ void __launch_bounds__(kRowsThreads, 1)
+constexpr int kRowsSumThreads = kRowsThreads + 128;   // + warps 10..13: column sums of the A tiles in flight
+
+template <bool kBf16>
+__device__ __forceinline__ void rows_add_pair(uint32_t packed, float& a0, float& a1) {
+  if (kBf16) {
+    asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.bf16 %0, lo, %0;\nadd.rn.f32.bf16 %1, hi, %1;\n}"
+        : "+f"(a0), "+f"(a1) : "r"(packed));
+  } else {
+    asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nadd.rn.f32.f16 %0, lo, %0;\nadd.rn.f32.f16 %1, hi, %1;\n}"
+        : "+f"(a0), "+f"(a1) : "r"(packed));
+  }
+}
+
+// Warps 10..13 of the kGroupSum variant: per-cloud column sums of segment 0 (<= 256 channels), taken from
+// its [128 rows][64 channels] tiles while they sit in the ring (first column tile of a row tile only; a row
+// tile lies inside one cloud).  Eight consecutive lanes read the eight 16-byte groups of one row (conflict
+// free under the 128-byte swizzle), a warp covers 4 rows per trip, the four warps 16; lanes are then folded
+// by two shuffles, warps through shared memory (the bias staging area, unused by a dgrad), and one atomic
+// per channel and row tile goes to group_sum.
+template <int kOut>
+__device__ __forceinline__ void rows_group_sums(const RowsParams& p, const RowsSmem& L, RowsTail* st, int warp, int lane) {
+  const RowsWork wk = rows_work(p);
+  const int cw = warp - 10;
+  const uint32_t g8 = static_cast<uint32_t>(lane) & 7u;     // 16-byte group = channels 8 g8 .. 8 g8 + 7
+  const int rsub = lane >> 3;                              // row inside the warp's 4-row trip
+  const int chunks0 = p.seg_k[0] / kBlockK;                // <= 4
+  int total_chunks = 0;
+  for (int s = 0; s < p.num_seg; ++s) total_chunks += p.seg_k[s] / kBlockK;
+  float* red = L.bias;                                     // [4 warps][256 channels]
+  const int64_t rpg = p.rows_per_group;
+  int stage = 0;
+  uint32_t phase = 0;
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  int64_t cur_g = -1;
+  auto flush = [&]() {                                     // warp-uniform: all four warps walk the same items
+    if (cur_g < 0) return;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = acc[c4][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        acc[c4][e] = v;
+      }
+    named_barrier_sync(5, 128);                            // the previous flush's readers are done with red
+    if (lane < 8) {
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4)
+        if (c4 < chunks0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) red[cw * 256 + c4 * 64 + lane * 8 + e] = acc[c4][e];
+        }
+    }
+    named_barrier_sync(5, 128);
+    for (int ch = cw * 32 + lane; ch < p.seg_k[0]; ch += 128)
+      atomicAdd(p.group_sum + cur_g * p.seg_k[0] + ch, red[ch] + red[256 + ch] + red[512 + ch] + red[768 + ch]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  };
+  for (int64_t t = wk.first; t < wk.count; t += wk.stride) {
+    const int64_t tm = wk.tm(t);
+    const bool take = wk.tn(t) == 0 && tm * kTileM < p.rows;
+    if (take) {
+      const int64_t g = (tm * kTileM) / rpg;
+      if (g != cur_g) { flush(); cur_g = g; }
+    }
+    for (int c = 0; c < total_chunks; ++c) {
+      mbar_wait(&st->full[stage], phase);
+      if (take && c < chunks0) {
+        const uint8_t* tile = L.stages + stage * p.stage_bytes;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          if (c4 == c) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t rr = static_cast<uint32_t>(16 * i + 4 * cw + rsub);
+              const uint4 q = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((g8 ^ (rr & 7u)) << 4));
+              rows_add_pair<kOut == PCADV_BF16>(q.x, acc[c4][0], acc[c4][1]);
+              rows_add_pair<kOut == PCADV_BF16>(q.y, acc[c4][2], acc[c4][3]);
+              rows_add_pair<kOut == PCADV_BF16>(q.z, acc[c4][4], acc[c4][5]);
+              rows_add_pair<kOut == PCADV_BF16>(q.w, acc[c4][6], acc[c4][7]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&st->empty[stage]);
+      if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+    }
+  }
+  flush();
+}
+
+template <int kAct, int kOut, int kAdd, bool kMaskBits, bool kRowMax = false, bool kGroupSum = false>
+__global__ void __launch_bounds__(kGroupSum ? kRowsSumThreads : kRowsThreads, 1)
 tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   const RowsSmem L = carve_rows(smem_raw, p);
@@ -293,6 +403,8 @@ tc_rows_lean_kernel(const __grid_constant__ TensorMaps maps, const RowsParams p)
     if (lane == 0) rows_producer(maps, p, L, st, num_tiles);
   } else if (warp == 1) {
     if (lane == 0) rows_mma(p, L, st, tmem_base, num_tiles);
+  } else if (kGroupSum && warp >= 10) {
+    rows_group_sums<kOut>(p, L, st, warp, lane);
   } else {
     const int ew = warp - 2;
     const int quarter = warp & 3;
@@ -518,6 +630,8 @@ static RowsKernel pick_lean(int act, int add, bool maskbits) {
   if (act == PCADV_ACT_NONE && add == kAddBias) return tc_rows_lean_kernel<PCADV_ACT_NONE, kOut, kAddBias, false>;
   return nullptr;
 }
+template <int kOut>
+static RowsKernel lean_group_sum() { return tc_rows_lean_kernel<PCADV_ACT_NONE, kOut, kAddNone, true, false, true>; }
 // max over channels only (no stored output): the discriminators' last layer
 static RowsKernel lean_rowmax() { return tc_rows_lean_kernel<PCADV_ACT_NONE, PCADV_F16, kAddBias, false, true>; }
 
@@ -902,6 +1016,16 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
     lean = lean_rowmax();
   PCADV_CHECK_ARG(lean || (!a.bits_out && !p.mask_bits),
                   "tc_linear: bit masks are only implemented for the lean layer shapes");
+  int threads = kRowsThreads;
+  if (a.seg0_group_sum) {
+    PCADV_CHECK_ARG(lean && lean != lean_rowmax() && p.mask_bits && a.act == PCADV_ACT_NONE && !a.bias && !a.group_bias &&
+                        !a.bits_out && a.rows_per_group > 0 && a.rows_per_group % kTileM == 0 &&
+                        a.rows % a.rows_per_group == 0 && a.seg[0].k <= 256,
+                    "tc_linear: seg0_group_sum needs the mask_bits dgrad shape, rows_per_group %% 128 == 0 and seg[0].k <= 256");
+    lean = out_dt == PCADV_F16 ? lean_group_sum<PCADV_F16>() : lean_group_sum<PCADV_BF16>();
+    p.group_sum = a.seg0_group_sum;
+    threads = kRowsSumThreads;
+  }
   p.tma_mask = (!lean && p.tma_out && a.mask && a.mask_act != PCADV_ACT_NONE && out_dt != PCADV_F32 &&
                 a.mask_dtype != PCADV_F32 && tma_compatible(a.mask, a.mask_dtype, a.ld_mask)) ? 1 : 0;
   if (p.tma_mask) {
@@ -919,7 +1043,7 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
   int nst = kRowsMaxStages;
   while (nst > 2 && rows_smem_bytes(nst, p.stage_bytes, p.nslabs) > static_cast<size_t>(kRowsSmemMax)) --nst;
   int epi_warps = kEpiWarps;
-  if (lean && lean != lean_rowmax() && ktot >= 512) {
+  if (lean && lean != lean_rowmax() && !a.seg0_group_sum && ktot >= 512) {
     // Deep-K layers (fc1: K = 960): a tile's MMAs take several microseconds, so ONE epilogue half with one
     // slab per warp keeps up with both TMEM buffers, and the 48 KB it frees is one more ring stage
     // (measured: fc1 0.564 -> 0.555 ms, the K = 768 dgrad 0.324 -> 0.313 ms per 2^20 points).
@@ -945,7 +1069,7 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
   static int pair_mode = -1;
   if (pair_mode < 0) { const char* e = getenv("PCADV_ROWS_PAIR"); pair_mode = e ? atoi(e) : 0; }   // 0 off, 1 wide weight tiles, 2 all lean launches
   const bool wide_w = static_cast<int64_t>(ktot) * p.bn >= 256 * 256;
-  if (lean && lean != lean_rowmax() && pair_mode > 0 && (wide_w || pair_mode == 2) && p.bn % 16 == 0 &&
+  if (lean && lean != lean_rowmax() && !a.seg0_group_sum && pair_mode > 0 && (wide_w || pair_mode == 2) && p.bn % 16 == 0 &&
       p.tiles_m >= 4 && num_sms() >= 2) {
     if (int rc = encode_tmap_2d(&maps.w_half, a.w, dt, a.n, ktot, a.ldw, kBlockK, p.bn / 2)) return rc;
     cudaLaunchConfig_t cfg = {};
@@ -976,7 +1100,7 @@ int tc_rows(const pcadv_linear_args& a, cudaStream_t s) {
     }
   }
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  k<<<grid, kRowsThreads, smem, s>>>(maps, p);
+  k<<<grid, threads, smem, s>>>(maps, p);
   PCADV_LAUNCHED();
   return 0;
 }

@@ -35,6 +35,9 @@ _G0, _G1, _C1 = 960, 3008, 3024                                       # global /
 # (e.g. "fc4,fc3,fc2,l4,l3,l2,l1").
 _LEVELS = frozenset(x for x in os.environ.get("PCADV_LEVELS", "fc4,fc3").split(",") if x)
 
+# d(cbias) as a by-product of the dz5 dgrad launch instead of a separate column-sum pass (tuning aid: PCADV_DCB_FROM_DGRAD=0)
+_DCB_FROM_DGRAD = os.environ.get("PCADV_DCB_FROM_DGRAD", "1") != "0"
+
 HEAD_GAIN = 256.0        # the fused CE head stores 256 * (softmax - onehot) as the 16-bit dz
 
 
@@ -342,6 +345,19 @@ class SegFunction(torch.autograd.Function):
         dw1 = pool.take(256, _C1) if need_w1 else None
         db1 = pool.take(256) if need_b1 else None
         dcb = pool.take(B, 256)                                        # d(cbias), scaled
+        # d(cbias) = the per-cloud column sums of dz_fc1.  Where the dense part of dz5 (below) can take them as a
+        # by-product of its pass over dz_fc1 it runs first, and fc1's weight gradient needs no separate
+        # column-sum pass over dz_fc1 (group_colsum16: 1 GB per step at cfg5).
+        s5 = _SLICES[4]
+        wt5 = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512, [256])
+        dz5_dense = None
+        inplace5 = ops.maxpool_inplace_eligible(512, N, 2048)
+        want_dcb = dcb
+        if _DCB_FROM_DGRAD and inplace5 and ops.group_sum_eligible(prec, [dz_fc1], wt5, 512, xbits[4], N):
+            dz5_dense, _, _ = ops.linear([dz_fc1], wt5, mask=xs[4], mask_act=ACT_RELU, out_dtype=prec.act_dtype,
+                                         engine=prec.engine, mask_bits=xbits[4], rows_per_group=N,
+                                         seg0_group_sum=dcb)
+            want_dcb = None
         # trunk levels that go through pcadv_backlevel also form their slice of fc1's weight gradient
         # (dz_fc1^T x_k); fc1's own wgrad launch then covers the remaining x segments only
         fused = [False] * 5
@@ -352,7 +368,7 @@ class SegFunction(torch.autograd.Function):
                     ops.backlevel_eligible(prec, [W[name].shape[0], dz_fc1.shape[1]], xs[li - 1], xbits[li - 1])
         rest = [i for i in range(5) if not fused[i]]
         if need_w1 and len(rest) == 5:
-            ops.wgrad(dz_fc1, xs, dw=dw1[:, :_G0], dgroup_bias=dcb, rows_per_group=N, scale=inv,
+            ops.wgrad(dz_fc1, xs, dw=dw1[:, :_G0], dgroup_bias=want_dcb, rows_per_group=N, scale=inv,
                       engine=prec.engine)
         else:
             # runs of adjacent unfused segments share one launch (their dw columns are contiguous)
@@ -364,10 +380,10 @@ class SegFunction(torch.autograd.Function):
                     j += 1
                 c0, c1 = _SLICES[rest[i]][0], _SLICES[rest[j]][1]
                 ops.wgrad(dz_fc1, [xs[q] for q in rest[i:j + 1]], dw=dw1[:, c0:c1],
-                          dgroup_bias=dcb if first else None, rows_per_group=N, scale=inv, engine=prec.engine)
+                          dgroup_bias=want_dcb if first else None, rows_per_group=N, scale=inv, engine=prec.engine)
                 first = False
                 i = j + 1
-            if first:                                                  # nothing left for fc1's own launch
+            if first and want_dcb is not None:                         # nothing left for fc1's own launch
                 ops.wgrad(dz_fc1, [], dgroup_bias=dcb, rows_per_group=N, scale=inv, engine=prec.engine)
         if need_w1 or need_b1:
             ops.wgrad(dcb, [g, cls2] if need_w1 else [], dw=dw1[:, _G0:_C1] if need_w1 else None,
@@ -382,13 +398,15 @@ class SegFunction(torch.autograd.Function):
         dw6 = pool.take(2048, 512) if need["conv6.weight"] else None
         db6 = pool.take(2048) if need["conv6.bias"] else None
         # ---- trunk: dz_k = relu'(x_k) * ([dz_{k+1} | dz_fc1] @ [W_{k+1}; fc1.W[:, slice_k]]) --
-        s5 = _SLICES[4]
-        wt = dgrad_weight(prec, [W["fc1"][:, s5[0]:s5[1]]], 512, [256])
+        wt = wt5
         w6 = compute_weight(prec, W["conv6"], [512], 2048)
-        if ops.maxpool_inplace_eligible(512, N, 2048):
+        if inplace5:
             # dense part first; the max-pool's sparse part (argmax rows only) is added in place
-            dz, _, _ = ops.linear([dz_fc1], wt, mask=xs[4], mask_act=ACT_RELU,
-                                  out_dtype=prec.act_dtype, engine=prec.engine, mask_bits=xbits[4])
+            if dz5_dense is not None:
+                dz = dz5_dense
+            else:
+                dz, _, _ = ops.linear([dz_fc1], wt, mask=xs[4], mask_act=ACT_RELU,
+                                      out_dtype=prec.act_dtype, engine=prec.engine, mask_bits=xbits[4])
             ops.maxpool_bwd(dg, g, idx, xs[4], w6, N, act=ACT_RELU, dw=dw6, dbias=db6,
                             dz_inout=dz, prev_act=ACT_RELU, scale=inv)
         else:

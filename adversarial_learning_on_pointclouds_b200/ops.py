@@ -135,11 +135,12 @@ def tc_eligible(segs, w, n):
 def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None, act=ACT_NONE,
            slope=0.0, mask=None, mask_act=ACT_NONE, mask_slope=0.0, out_dtype=torch.float32,
            out_scale=None, want_out=True, colmax=False, rowmax=False, engine=ENGINE_SIMT, n=None,
-           bits_out=None, mask_bits=None):
+           bits_out=None, mask_bits=None, seg0_group_sum=None):
     """See ``pcadv_linear`` in include/pcadv.h.  Returns (out | None, colmax_key |
     None, rowmax_key | None).  ``bits_out``: a ``new_bits(rows, n)`` tensor that receives the
     sign bits of the output; ``mask_bits``: such a tensor used instead of ``mask`` (both only
-    where ``bits_eligible`` holds)."""
+    where ``bits_eligible`` holds).  ``seg0_group_sum``: fp32 [rows / rows_per_group, segs[0] width] that receives
+    (+=) the per-cloud column sums of the first segment as a by-product (``group_sum_eligible`` shapes only)."""
     a = _lib.LinearArgs()
     rows = segs[0].shape[0]
     n = int(n if n is not None else w.shape[0])
@@ -187,6 +188,10 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
             raise ValueError("bits_out needs a 16-bit output")
         a.bits_out, a.ld_bits_out = C.c_void_p(bits_out.data_ptr()), bits_out.stride(0)
     a.out_scale = _f32(out_scale) if out_scale is not None else None
+    if seg0_group_sum is not None:
+        if not use_bits or rows_per_group <= 0:
+            raise ValueError("seg0_group_sum needs the mask_bits dgrad shape and rows_per_group")
+        a.seg0_group_sum = _f32(seg0_group_sum, (rows // rows_per_group) * segs[0].shape[1])
     out = ckey = rkey = None
     a.out_dtype = _DT[out_dtype]
     if want_out:
@@ -207,6 +212,14 @@ def linear(segs, w, *, bias=None, group_bias=None, rows_per_group=0, addend=None
     if rows > 0:                                   # an empty batch launches nothing
         _call(tag, _lib.lib().pcadv_linear, C.byref(a), _stream(), rows=rows)
     return out, ckey, rkey
+
+
+def group_sum_eligible(prec, segs, w, n, mask_bits, rows_per_group):
+    """Shapes for which ``linear(..., seg0_group_sum=...)`` works: the tensor-core mask-bits dgrad over 16-bit
+    operands, clouds that are whole 128-row tiles, a first segment of at most 256 channels."""
+    return (prec.engine == ENGINE_TC and prec.act_dtype != torch.float32 and mask_bits is not None and n % 64 == 0
+            and rows_per_group > 0 and rows_per_group % 128 == 0 and segs[0].shape[0] % rows_per_group == 0
+            and segs[0].shape[1] <= 256 and tc_eligible(segs, w, n))
 
 
 def chain_eligible(x, widths, last_f32=False, allow_serial=False):

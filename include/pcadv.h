@@ -106,6 +106,11 @@ typedef struct pcadv_linear_args {
   int64_t ld_bits_out;
   const uint32_t* mask_bits;
   int64_t ld_mask_bits;
+  /* Optional by-product (tensor-core engine, the mask_bits dgrad shape, rows_per_group % 128 == 0, seg[0].k <= 256):
+   *   seg0_group_sum[g, k] += sum_{r in cloud g} seg[0][r, k]        (fp32 [rows / rows_per_group, seg[0].k], NOT scaled)
+   * taken from the tiles of segment 0 while they pass through shared memory -- for PointNetSeg the gradient of
+   * fc1's per-cloud bias (models/pointnet.py:304-309 under autograd), without a separate pass over dz_fc1. */
+  float* seg0_group_sum;
 } pcadv_linear_args;
 
 int pcadv_linear(const pcadv_linear_args* a, void* stream);

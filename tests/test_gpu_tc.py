@@ -360,3 +360,29 @@ def test_backlevel_does_not_overrun_caller_buffers(rows, ks, n):
     assert rel_err(out, torch.cat(segs, 1).double() @ w.double().t()) < 1e-3
     assert rel_err(dws[-1], segs[-1].double().t() @ x.double()) < 1e-5
     assert rel_err(db, segs[0].double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,ks,n,rpg", [(4096, [256], 512, 1024), (2560, [128, 64], 128, 640), (1024, [64], 64, 128)])
+def test_tc_linear_group_sum_byproduct(dtype, rows, ks, n, rpg):
+    """seg0_group_sum: the per-cloud column sums of the first segment come out of the mask-bits dgrad
+    launch (exact fp32 sums of the 16-bit values), the dgrad result itself is unchanged."""
+    segs = [_rand((rows, k), 90 + i, dtype) for i, k in enumerate(ks)]
+    w = _rand((n, sum(ks)), 93, dtype, 0.1)
+    y = _rand((rows, n), 94, dtype).relu()
+    bits = ops.new_bits(rows, n, DEV)
+    pos = (y.float() > 0).reshape(rows, n // 32, 32).long()
+    j = torch.arange(32, device=DEV)
+    words = (pos << ((j >> 1) + 16 * (j & 1))).sum(2)
+    bits.copy_((words - ((words >> 31) << 32)).to(torch.int32))
+    ref, _, _ = ops.linear(segs, w, mask=y, mask_act=ACT_RELU, out_dtype=dtype, engine=ENGINE_TC, mask_bits=bits)
+    gs = torch.zeros((rows // rpg, ks[0]), device=DEV)
+    out, _, _ = ops.linear(segs, w, mask=y, mask_act=ACT_RELU, out_dtype=dtype, engine=ENGINE_TC, mask_bits=bits,
+                           rows_per_group=rpg, seg0_group_sum=gs)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert rel_err(gs, segs[0].double().reshape(rows // rpg, rpg, -1).sum(1)) < 1e-6
+    # accumulates
+    ops.linear(segs, w, mask=y, mask_act=ACT_RELU, out_dtype=dtype, engine=ENGINE_TC, mask_bits=bits,
+               rows_per_group=rpg, seg0_group_sum=gs)
+    assert rel_err(gs, 2 * segs[0].double().reshape(rows // rpg, rpg, -1).sum(1)) < 1e-6
